@@ -1,0 +1,78 @@
+#!/usr/bin/env python
+"""Mint the golden fixtures for the CNN-backbone forward path.
+
+Runs the REFERENCE'S OWN model files (loaded by path from /root/reference,
+unmodified, through oracle/ref_loader.py + oracle/tlx_compat.py) on the seeded
+weights of tlxcv_b200/testing.py and seeded synthetic images, and writes
+
+  tests/golden/<model>.npz   logits (or feature maps) + input spec + weight digest
+  tests/golden/manifests.json  ordered state-dict manifest (name -> shape) per model
+
+The reference has no tests or golden vectors of its own, so these
+files are the pin.  They can only be (re)generated where /root/reference is
+mounted; the GPU box uses the committed files.
+
+    python tests/golden/make_golden.py
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_loader  # noqa: E402
+from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, synthetic_images  # noqa: E402
+
+# model -> (n_images, image size)
+CASES = {
+    "resnet50": (4, 224),
+    "resnet18": (2, 224),
+    "resnext50_32x4d": (2, 224),
+    "mobilenet_v1": (2, 224),
+    "mobilenet_v2": (2, 224),
+    "darknet53_cls": (2, 224),
+    "darknet53_det": (1, 64),
+}
+MANIFEST_ONLY = ["resnet34", "resnet101", "wide_resnet50_2", "resnext50_64x4d"]
+
+
+def main():
+    torch.set_num_threads(os.cpu_count() or 1)
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    manifests = {}
+    for name in list(CASES) + MANIFEST_ONLY:
+        model = ref_loader.build(name)
+        manifest = [(k, list(v.shape)) for k, v in model.state_dict().items()]
+        manifests[name] = manifest
+        if name not in CASES:
+            continue
+        n, size = CASES[name]
+        sd = seeded_state_dict(model.state_dict(), name)
+        model.load_state_dict(sd)
+        model.set_eval()
+        x = synthetic_images(n, size)
+        with torch.no_grad():
+            y = model({"images": x}) if name == "darknet53_det" else model(x)
+        outs = y if isinstance(y, (list, tuple)) else [y]
+        arrays = {f"out{i}": o.numpy() for i, o in enumerate(outs)}
+        np.savez_compressed(
+            os.path.join(out_dir, f"{name}.npz"),
+            n=np.int64(n), size=np.int64(size),
+            weight_digest=np.array(state_dict_digest(sd)),
+            input_digest=np.array(state_dict_digest({"x": x})),
+            **arrays,
+        )
+        print(name, [tuple(o.shape) for o in outs], "std", float(outs[0].std()))
+    with open(os.path.join(out_dir, "manifests.json"), "w") as f:
+        json.dump(manifests, f)
+    print("wrote", out_dir)
+
+
+if __name__ == "__main__":
+    main()
