@@ -1,0 +1,524 @@
+// Implicit-GEMM convolution for sm_100a: NHWC bf16 activations, TMA-staged operand tiles,
+// tcgen05.mma accumulating fp32 in TMEM, fused epilogue
+//     y = act2( act1( acc * scale + shift ) + residual )
+// which is GroupConv2d + BatchNorm2d(eval) + ReLU/ReLU6/LeakyReLU + residual add + ReLU of the
+// reference (classification/resnet.py:142-156, resnext.py:109-119, mobilenetv2.py:36-40,
+// detection/backbones/darknet.py:54-58,155-159) in one kernel.
+//
+// GEMM view:  D[M = N*P*Q pixels][Cout] = A[M][K = R*S*Cin] * W[Cout][K]^T
+//   A tile  128 pixels x 64 channels of ONE filter tap  (16 KB, SWIZZLE_128B, K-major)
+//             kModeTiled    plain 2-D TMA box of the [M][C] matrix (1x1 stride 1)
+//             kModeIm2col   im2col-mode TMA: the hardware walks 128 consecutive output pixels of
+//                           the NHWC tensor (wrapping rows / images, zero-filling the halo)
+//             kModeGatherC4 stems with C_in = 3 (stored as 4): four producer warps gather the
+//                           filter rows from NHWC4 global memory straight into the swizzled tile
+//   B tile  BLOCK_N filters x 64 K-elements (K-major, SWIZZLE_128B) from the packed weights
+//   D       BLOCK_N fp32 TMEM columns x 128 lanes, double buffered (epilogue of tile i overlaps
+//           the main loop of tile i+1)
+// Warp roles (persistent CTA, one per SM): w0 TMA producer, w1 MMA issuer (one thread),
+// w2 TMEM allocator, w4-7 epilogue (TMEM -> registers -> smem transpose -> coalesced 16 B stores),
+// w8-11 gather producers (kModeGatherC4 only).
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tlxcv {
+
+namespace {
+
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;
+constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
+constexpr int kStagingBytes = 4 * 2048;         // 4 epilogue warps x (32 rows x 64 B)
+constexpr int kBarrierBytes = 256;
+constexpr int kMaxStages = 8;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: a power of two >= 32
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+};
+
+struct PipeState {
+  uint32_t stage = 0, phase = 0;
+  __device__ __forceinline__ void advance(uint32_t n_stages) {
+    if (++stage == n_stages) {
+      stage = 0;
+      phase ^= 1;
+    }
+  }
+};
+
+template <int BLOCK_N, int MODE>
+__global__ void __launch_bounds__(MODE == kModeGatherC4 ? 384 : 256, 1)
+conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const ConvKernelParams p) {
+  using C = Cfg<BLOCK_N>;
+  extern __shared__ uint8_t smem_raw[];
+  // SWIZZLE_128B operand tiles need 1024-byte alignment
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* staging = smem + C::kStages * C::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  uint64_t* full_bar = bars;                       // [kStages]  operands landed
+  uint64_t* empty_bar = bars + kMaxStages;         // [kStages]  MMAs that read the stage retired
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]        accumulator complete
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]        accumulator drained by the epilogue
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int num_tiles = p.m_tiles * p.n_tiles;
+
+  if (warp == 0 && lane == 0) {
+    if (MODE != kModeGatherC4) tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < C::kStages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), MODE == kModeGatherC4 ? 1 + 128 : 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<C::kTmemCols>(smem_u32(tmem_ptr_smem));
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      PipeState ps;
+      const int PQ = p.P * p.Q;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int m0 = m_tile * kBlockM, n0 = n_tile * BLOCK_N;
+        int img = 0, base_h = 0, base_w = 0;
+        if (MODE == kModeIm2col) {
+          img = m0 / PQ;
+          const int rem = m0 - img * PQ;
+          const int op = rem / p.Q, oq = rem - op * p.Q;
+          base_h = op * p.stride - p.pad;
+          base_w = oq * p.stride - p.pad;
+        }
+        const int c_base = p.a_chan_from_n ? n_tile * BLOCK_N : 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[ps.stage]);
+          const uint32_t a_dst = smem_u32(smem + ps.stage * C::kStageBytes);
+          const uint32_t b_dst = a_dst + kABytes;
+          mbar_arrive_expect_tx(bar, MODE == kModeGatherC4 ? C::kBBytes : C::kStageBytes);
+          if (MODE == kModeTiled) {
+            tma_load_2d(a_dst, &tmapA, bar, kb * kBlockK, m0);
+          } else if (MODE == kModeIm2col) {
+            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
+            const int r = tap / p.S, s = tap - r * p.S;
+            tma_load_im2col_4d(a_dst, &tmapA, bar, c_base + cb * kBlockK, base_w, base_h, img,
+                               static_cast<uint16_t>(s * p.dil), static_cast<uint16_t>(r * p.dil));
+          }
+          tma_load_2d(b_dst, &tmapB, bar, kb * kBlockK, n0);
+          ps.advance(C::kStages);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (one thread) =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+      PipeState ps;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(smem_u32(&full_bar[ps.stage]), ps.phase);
+          tcgen05_fence_after();
+          const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
+          const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
+          const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kABytes);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[ps.stage]));  // frees the smem stage when these MMAs retire
+          ps.advance(C::kStages);
+        }
+        umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator ready for the epilogue
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================== epilogue =====================
+    const int ew = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
+    uint8_t* stg = staging + ew * 2048;
+    const uint32_t stg_u32 = smem_u32(stg);
+    const int swz_own = (lane >> 1) & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int m0 = m_tile * kBlockM + ew * 32, n0 = n_tile * BLOCK_N;
+      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+      tcgen05_fence_after();
+#pragma unroll 1
+      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+        const int cbase = n0 + chunk * 32;
+        if (cbase >= p.Cout) break;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + j);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + j);
+          f[4 * j + 0] = apply_act(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x), p.act1, p.alpha1);
+          f[4 * j + 1] = apply_act(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), p.act1, p.alpha1);
+          f[4 * j + 2] = apply_act(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), p.act1, p.alpha1);
+          f[4 * j + 3] = apply_act(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), p.act1, p.alpha1);
+        }
+        if (p.residual != nullptr) {
+          // coalesced read of the 32 x 32 residual block (64 B row segments), transposed through smem
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (lane >> 2) + 8 * i, q4 = lane & 3;
+            const int gr = m0 + r, col = cbase + q4 * 8;
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (gr < p.M && col < p.Cout)
+              val = __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(gr) * p.Cout + col));
+            *reinterpret_cast<uint4*>(stg + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4)) = val;
+          }
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((j ^ swz_own) << 4));
+            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 rr = __bfloat1622float2(h[e]);
+              f[8 * j + 2 * e] += rr.x;
+              f[8 * j + 2 * e + 1] += rr.y;
+            }
+          }
+          __syncwarp();
+        }
+        if (p.act2 != TLXCV_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act2, p.alpha2);
+        }
+        if (p.out_f32) {
+          const int gr = m0 + lane;
+          if (gr < p.M) {
+            float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(gr) * p.Cout + cbase;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              if (cbase + 4 * j < p.Cout)
+                reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint4 o;
+            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
+            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
+            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ swz_own) << 4)) = o;
+          }
+          __syncwarp();
+          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = (lane >> 2) + 8 * i, q4 = lane & 3;
+            const int gr = m0 + r, col = cbase + q4 * 8;
+            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4));
+            if (gr < p.M && col < p.Cout)
+              *reinterpret_cast<uint4*>(outp + static_cast<size_t>(gr) * p.Cout + col) = val;
+          }
+          __syncwarp();
+        }
+      }
+      (void)stg_u32;
+      tcgen05_fence_before();
+      mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+      if (++acc == 2) {
+        acc = 0;
+        acc_phase ^= 1;
+      }
+    }
+  } else if (MODE == kModeGatherC4 && warp >= 8) {
+    // ===================== gather producers (C_in <= 4 stems) =====================
+    // K layout of one 64-wide block: r_per_kb filter rows x KR elements, element = s*4 + c.
+    const int t = threadIdx.x - 256;  // A-tile row owned by this thread
+    const int r_per_kb = kBlockK / p.KR;
+    const int chunks_per_row = p.KR / 8;  // 16 B chunks (two taps) per filter row
+    const int PQ = p.P * p.Q;
+    PipeState ps;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      const int m = m_tile * kBlockM + t;
+      const bool row_ok = m < p.M;
+      const int img = row_ok ? m / PQ : 0;
+      const int rem = m - img * PQ;
+      const int op = rem / p.Q, oq = rem - op * p.Q;
+      const int ih0 = op * p.stride - p.pad, iw0 = oq * p.stride - p.pad;
+      const uint2* img_base = reinterpret_cast<const uint2*>(p.in_c4) + static_cast<size_t>(img) * p.H * p.W;
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+        uint8_t* a_row = smem + ps.stage * C::kStageBytes + t * 128;
+        for (int slot = 0; slot < r_per_kb; ++slot) {
+          const int r = kb * r_per_kb + slot;
+          const int ih = ih0 + r * p.dil;
+          const bool rok = row_ok && r < p.R && ih >= 0 && ih < p.H;
+          const uint2* rowp = img_base + static_cast<size_t>(rok ? ih : 0) * p.W;
+          for (int j = 0; j < chunks_per_row; ++j) {
+            uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
+            const int s0 = 2 * j, s1 = 2 * j + 1;
+            const int w0 = iw0 + s0 * p.dil, w1 = iw0 + s1 * p.dil;
+            if (rok && s0 < p.S && w0 >= 0 && w0 < p.W) lo = __ldg(rowp + w0);
+            if (rok && s1 < p.S && w1 >= 0 && w1 < p.W) hi = __ldg(rowp + w1);
+            const int chunk = slot * chunks_per_row + j;
+            *reinterpret_cast<uint4*>(a_row + ((chunk ^ (t & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
+          }
+        }
+        fence_proxy_async_smem();  // make the generic-proxy stores visible to tcgen05.mma's smem reads
+        mbar_arrive(smem_u32(&full_bar[ps.stage]));
+        ps.advance(C::kStages);
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tcgen05_fence_after();
+    tmem_dealloc<C::kTmemCols>(tmem_base);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+using EncodeIm2colFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+EncodeTiledFn g_encode_tiled = nullptr;
+EncodeIm2colFn g_encode_im2col = nullptr;
+
+std::string load_driver_entry_points() {
+  if (g_encode_tiled && g_encode_im2col) return "";
+  cudaDriverEntryPointQueryResult qres;
+  void* fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return "cuTensorMapEncodeTiled is not available from the driver";
+  g_encode_tiled = reinterpret_cast<EncodeTiledFn>(fn);
+  fn = nullptr;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return "cuTensorMapEncodeIm2col is not available from the driver";
+  g_encode_im2col = reinterpret_cast<EncodeIm2colFn>(fn);
+  return "";
+}
+
+std::string encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
+                      uint32_t box_inner, uint32_t box_outer) {
+  cuuint64_t dims[2] = {inner, outer};
+  cuuint64_t strides[1] = {row_bytes};
+  cuuint32_t box[2] = {box_inner, box_outer};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeTiled failed (%d) dims=(%llu,%llu) stride=%llu box=(%u,%u)", int(r),
+             (unsigned long long)inner, (unsigned long long)outer, (unsigned long long)row_bytes, box_inner, box_outer);
+    return buf;
+  }
+  return "";
+}
+
+std::string encode_im2col(CUtensorMap* map, const void* base, int N, int H, int W, int C, int R, int S, int stride,
+                          int pad, int dil) {
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  // bounding box of base pixels: lower = -pad, upper = pad - (filter-1)*dilation  (W, H order)
+  int lower[2] = {-pad, -pad};
+  int upper[2] = {pad - (S - 1) * dil, pad - (R - 1) * dil};
+  cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
+  CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
+                               upper, kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    char buf[256];
+    snprintf(buf, sizeof buf, "cuTensorMapEncodeIm2col failed (%d) NHWC=(%d,%d,%d,%d) RS=(%d,%d) stride=%d pad=%d", int(r),
+             N, H, W, C, R, S, stride, pad);
+    return buf;
+  }
+  // Known driver quirk for small tensors (the CUTLASS im2col descriptor builder applies the same fix).
+  int drv = 0;
+  if (cudaDriverGetVersion(&drv) == cudaSuccess && drv <= 13010) {
+    const size_t bytes = static_cast<size_t>(N) * H * W * C * 2;
+    if (bytes < 131072) reinterpret_cast<uint64_t*>(map)[1] &= ~(1ull << 21);
+  }
+  return "";
+}
+
+template <int BLOCK_N, int MODE>
+cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
+  conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.p);
+  return cudaGetLastError();
+}
+
+template <int BLOCK_N, int MODE>
+cudaError_t set_attr_t() {
+  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                              Cfg<BLOCK_N>::kSmem);
+}
+
+int smem_for(int block_n) {
+  return block_n == 256 ? Cfg<256>::kSmem : (block_n == 128 ? Cfg<128>::kSmem : Cfg<64>::kSmem);
+}
+
+}  // namespace
+
+int tc_conv_mode(int Cin, int R, int S, int stride, int pad, int groups) {
+  if (Cin <= 4) return kModeGatherC4;
+  if (R == 1 && S == 1 && stride == 1 && pad == 0 && groups == 1) return kModeTiled;
+  return kModeIm2col;
+}
+
+int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode) {
+  if (mode == kModeGatherC4) {
+    const int KR = (S * 4 <= 16) ? 16 : 32;
+    const int r_per_kb = kBlockK / KR;
+    return ((R + r_per_kb - 1) / r_per_kb) * kBlockK;
+  }
+  if (groups > 1) return R * S * kBlockK;
+  return R * S * ((Cin + kBlockK - 1) / kBlockK) * kBlockK;
+}
+
+cudaError_t tc_conv_set_attributes() {
+  cudaError_t e;
+#define TLXCV_SET(BN, MD) \
+  if ((e = set_attr_t<BN, MD>()) != cudaSuccess) return e;
+  TLXCV_SET(64, kModeTiled) TLXCV_SET(128, kModeTiled) TLXCV_SET(256, kModeTiled)
+  TLXCV_SET(64, kModeIm2col) TLXCV_SET(128, kModeIm2col) TLXCV_SET(256, kModeIm2col)
+  TLXCV_SET(64, kModeGatherC4) TLXCV_SET(128, kModeGatherC4)
+#undef TLXCV_SET
+  return cudaSuccess;
+}
+
+std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
+                            int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
+                            int pad, int dil, int groups, int force_block_n) {
+  std::string err = load_driver_entry_points();
+  if (!err.empty()) return err;
+  memset(&L, 0, sizeof L);
+  const int mode = tc_conv_mode(Cin, R, S, stride, pad, groups);
+  const int P = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int Q = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  const long long M = static_cast<long long>(N) * P * Q;
+  if (M <= 0 || M > 0x7fffffffLL) return "conv: output pixel count out of range";
+  ConvKernelParams& p = L.p;
+  p.M = static_cast<int>(M);
+  p.Cout = Cout;
+  p.S = S, p.R = R, p.P = P, p.Q = Q, p.H = H, p.W = W, p.stride = stride, p.pad = pad, p.dil = dil;
+  if (Cout % 8) return "conv: C_out must be a multiple of 8 on the tensor-core path";
+
+  int block_n;
+  if (mode == kModeGatherC4) {
+    if (S * 4 > 32) return "stem conv: filter width > 8 is not supported";
+    if (Cin_storage != 4) return "stem conv: input must be stored as NHWC4";
+    if (groups != 1) return "stem conv: groups must be 1";
+    p.KR = (S * 4 <= 16) ? 16 : 32;
+    p.num_kb = Ktot / kBlockK;
+    p.kb_per_tap = 1;
+    p.in_c4 = act_in;
+    block_n = Cout <= 64 ? 64 : 128;
+  } else if (groups > 1) {
+    const int cpg = Cin / groups;
+    if (Cin != Cout || cpg * groups != Cin || (kBlockK % cpg) != 0 || (Cin % kBlockK) != 0)
+      return "grouped conv: only C_in == C_out with channels-per-group dividing 64 is on the tensor-core path";
+    if (dil != 1) return "grouped conv: dilation must be 1";
+    p.a_chan_from_n = 1;
+    p.kb_per_tap = 1;
+    p.num_kb = R * S;
+    block_n = 64;
+  } else {
+    if (Cin % 8) return "conv: C_in must be a multiple of 8 on the tensor-core path";
+    p.kb_per_tap = (Cin + kBlockK - 1) / kBlockK;
+    p.num_kb = R * S * p.kb_per_tap;
+    // tile width: minimise (waves x per-tile MMA time); N=64 tiles are shared-memory-bandwidth limited
+    const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+    double best = 1e30;
+    block_n = 64;
+    for (int bn : {256, 128, 64}) {
+      if (bn > 64 && bn / 2 >= Cout) continue;  // do not pad C_out by 2x or more
+      const long long tiles = static_cast<long long>(m_tiles) * ((Cout + bn - 1) / bn);
+      const double waves = static_cast<double>((tiles + sm_count - 1) / sm_count);
+      const double mma = p.num_kb * 4.0 * std::max(bn / 2, 48);                       // cycles per tile (tensor pipe)
+      const double mem = (kABytes * p.num_kb + 2.0 * kBlockM * bn * 2) / 40.0;          // cycles per tile at ~40 B/clk/SM
+      const double cost = waves * (std::max(mma, mem) + 600.0);
+      if (cost < best) best = cost, block_n = bn;
+    }
+  }
+  if (force_block_n == 64 || force_block_n == 128 || force_block_n == 256) {
+    if (!(groups > 1 && force_block_n != 64) && !(mode == kModeGatherC4 && force_block_n == 256))
+      block_n = force_block_n;
+  }
+  if (Ktot != p.num_kb * kBlockK) return "conv: packed weight K does not match the kernel's K blocking";
+  p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  p.n_tiles = (Cout + block_n - 1) / block_n;
+  L.mode = mode;
+  L.block_n = block_n;
+  L.threads = mode == kModeGatherC4 ? 384 : 256;
+  L.smem = smem_for(block_n);
+  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
+  L.grid = static_cast<int>(std::min<long long>(tiles, sm_count));
+
+  // B: packed weights [Cout_pad][Ktot], K-major; Cout_pad is a multiple of 256 rows so any tile box is in bounds
+  const int cout_pad = ((Cout + 255) / 256) * 256;
+  err = encode_2d(&L.tmapB, packed_w, Ktot, cout_pad, static_cast<uint64_t>(Ktot) * 2, kBlockK, block_n);
+  if (!err.empty()) return err;
+  if (mode == kModeTiled) {
+    err = encode_2d(&L.tmapA, act_in, Cin, p.M, static_cast<uint64_t>(Cin_storage) * 2, kBlockK, kBlockM);
+  } else if (mode == kModeIm2col) {
+    if (Cin_storage != Cin) return "conv: padded channel storage is only supported for stems";
+    err = encode_im2col(&L.tmapA, act_in, N, H, W, Cin, R, S, stride, pad, dil);
+  } else {
+    L.tmapA = L.tmapB;  // unused
+  }
+  return err;
+}
+
+cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t st) {
+#define TLXCV_CASE(BN, MD) \
+  if (L.block_n == BN && L.mode == MD) return launch_t<BN, MD>(L, st);
+  TLXCV_CASE(64, kModeTiled) TLXCV_CASE(128, kModeTiled) TLXCV_CASE(256, kModeTiled)
+  TLXCV_CASE(64, kModeIm2col) TLXCV_CASE(128, kModeIm2col) TLXCV_CASE(256, kModeIm2col)
+  TLXCV_CASE(64, kModeGatherC4) TLXCV_CASE(128, kModeGatherC4)
+#undef TLXCV_CASE
+  return cudaErrorInvalidValue;
+}
+
+}  // namespace tlxcv

@@ -1,0 +1,471 @@
+// Memory-bound CUDA-core kernels of the CNN-backbone forward path (NHWC, 128-bit vectorised along
+// C), the one-time weight/BN preparation kernels, and the fp32 direct convolution used by the
+// fp32 validation mode.  Each replaces one tensorlayerx layer of the reference hot path:
+//   import/export_nchw  the NCHW fp32 tensors the reference passes in / gets back (layout pass, K7)
+//   maxpool_nhwc        nn.MaxPool2d(3,2,1)       classification/resnet.py:213-218, resnext.py:159-164
+//   gap_nhwc            nn.AdaptiveAvgPool2d(1)   resnet.py:227-231
+//   dwconv_nhwc         depthwise GroupConv2d + BN + ReLU6/ReLU  ops/ops_fusion.py:39-48, mobilenetv1.py:81-89
+//   argmax_rows         tlx.argmax(axis=-1)       tasks/image_classification.py:23
+#include <cfloat>
+
+#include "common.cuh"
+#include "kernels.h"
+
+namespace tlxcv {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int blocks_for(size_t work, int threads = kThreads) {
+  size_t b = (work + threads - 1) / threads;
+  return static_cast<int>(b < 1 ? 1 : (b > 0x7fffffffull ? 0x7fffffffull : b));
+}
+
+// ------------------------------------------------------------------------------------------------
+// weight / BN preparation (run once per plan)
+// ------------------------------------------------------------------------------------------------
+__global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int Cout,
+                                         int Cout_pad, int Cin, int R, int S, int groups, int mode, int Ktot) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<size_t>(Cout_pad) * Ktot) return;
+  const int o = static_cast<int>(idx / Ktot), k = static_cast<int>(idx % Ktot);
+  const int Cg = Cin / groups;
+  float v = 0.0f;
+  if (o < Cout) {
+    if (mode == kModeGatherC4) {
+      const int KR = (S * 4 <= 16) ? 16 : 32;
+      const int r_per_kb = 64 / KR;
+      const int kb = k / 64, within = k % 64;
+      const int r = kb * r_per_kb + within / KR, e = within % KR;
+      const int s = e / 4, c = e % 4;
+      if (r < R && s < S && c < Cin) v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s];
+    } else if (groups > 1) {
+      // 64-channel block-diagonal expansion: K slot (tap, cl) holds input channel 64*(o/64)+cl
+      const int tap = k / 64, cl = k % 64;
+      const int r = tap / S, s = tap % S;
+      const int c = (o / 64) * 64 + cl;
+      const int cpg_out = Cout / groups;
+      if (c < Cin && c / Cg == o / cpg_out) v = w[((static_cast<size_t>(o) * Cg + (c % Cg)) * R + r) * S + s];
+    } else {
+      const int kpt = ((Cin + 63) / 64) * 64;
+      const int tap = k / kpt, c = k % kpt;
+      const int r = tap / S, s = tap % S;
+      if (c < Cin) v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s];
+    }
+  }
+  dst[idx] = __float2bfloat16_rn(v);
+}
+
+__global__ void pack_linear_weights_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int F, int Kout,
+                                           int Kout_pad) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= static_cast<size_t>(Kout_pad) * F) return;
+  const int o = static_cast<int>(idx / F), f = static_cast<int>(idx % F);
+  dst[idx] = __float2bfloat16_rn(o < Kout ? w[static_cast<size_t>(f) * Kout + o] : 0.0f);
+}
+
+__global__ void pack_conv_weights_f32_kernel(const float* __restrict__ w, float* __restrict__ dst, int Cout, int Cg,
+                                             int R, int S) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  const size_t total = static_cast<size_t>(Cout) * Cg * R * S;
+  if (idx >= total) return;
+  // dst [R][S][Cg][Cout]
+  const int o = static_cast<int>(idx % Cout);
+  size_t t = idx / Cout;
+  const int c = static_cast<int>(t % Cg);
+  t /= Cg;
+  const int s = static_cast<int>(t % S), r = static_cast<int>(t / S);
+  dst[idx] = w[((static_cast<size_t>(o) * Cg + c) * R + r) * S + s];
+}
+
+template <typename T>
+__global__ void pack_dw_weights_kernel(const float* __restrict__ w, T* __restrict__ dst, int C, int RS) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= C * RS) return;
+  const int c = idx % C, t = idx / C;
+  dst[idx] = from_f32<T>(w[static_cast<size_t>(c) * RS + t]);
+}
+
+__global__ void fold_bn_kernel(float* scale, float* shift, const float* gamma, const float* beta, const float* mean,
+                               const float* var, const float* bias, float eps, int K, int K_pad) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K_pad) return;
+  float sc = 0.0f, sh = 0.0f;
+  if (k < K) {
+    const float b = bias ? bias[k] : 0.0f;
+    if (gamma) {
+      // same operation order as F.batch_norm's eval formula: (x - mean) * rsqrt(var + eps) * gamma + beta
+      sc = gamma[k] / sqrtf(var[k] + eps);
+      sh = beta[k] + (b - mean[k]) * sc;
+    } else {
+      sc = 1.0f;
+      sh = b;
+    }
+  }
+  scale[k] = sc;
+  shift[k] = sh;
+}
+
+// ------------------------------------------------------------------------------------------------
+// layout passes
+// ------------------------------------------------------------------------------------------------
+// small-C import (C <= 4): one thread per pixel, planes read coalesced, one 8 B / 16 B store
+template <typename T>
+__global__ void import_nchw_smallc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, size_t HW,
+                                          size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const size_t n = idx / HW, hw = idx % HW;
+  const float* s = src + n * C * HW + hw;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < C; ++c) v[c] = __ldg(s + c * HW);
+  if constexpr (sizeof(T) == 2) {
+    uint2 o = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    reinterpret_cast<uint2*>(dst)[idx] = o;
+  } else {
+    reinterpret_cast<float4*>(dst)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+// general transpose [N][C][HW] fp32 -> [N][HW][C] T through a 32x32 smem tile
+template <typename T>
+__global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const float* s = src + static_cast<size_t>(n) * C * HW;
+  T* d = dst + static_cast<size_t>(n) * HW * C;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    tile[i][threadIdx.x] = (c < C && p < HW) ? __ldg(s + static_cast<size_t>(c) * HW + p) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    if (p < HW && c < C) d[static_cast<size_t>(p) * C + c] = from_f32<T>(tile[threadIdx.x][i]);
+  }
+}
+
+template <typename T>
+__global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
+  const T* s = src + static_cast<size_t>(n) * HW * C;
+  float* d = dst + static_cast<size_t>(n) * C * HW;
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int p = p0 + i, c = c0 + threadIdx.x;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? to_f32(s[static_cast<size_t>(p) * C + c]) : 0.0f;
+  }
+  __syncthreads();
+  for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+    const int c = c0 + i, p = p0 + threadIdx.x;
+    if (c < C && p < HW) d[static_cast<size_t>(c) * HW + p] = tile[threadIdx.x][i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// pooling
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C8, int P, int Q,
+                                    int k, int stride, int pad, size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % C8);
+  size_t t = idx / C8;
+  const int q = static_cast<int>(t % Q);
+  t /= Q;
+  const int pp = static_cast<int>(t % P);
+  const size_t n = t / P;
+  float m[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = -FLT_MAX;  // padding behaves as -inf (F.max_pool2d)
+  const int h0 = pp * stride - pad, w0 = q * stride - pad;
+  for (int r = 0; r < k; ++r) {
+    const int h = h0 + r;
+    if (h < 0 || h >= H) continue;
+    for (int s = 0; s < k; ++s) {
+      const int w = w0 + s;
+      if (w < 0 || w >= W) continue;
+      float v[8];
+      Vec8<T>::load(src + ((n * H + h) * W + w) * static_cast<size_t>(C8) * 8 + c8 * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], v[i]);
+    }
+  }
+  Vec8<T>::store(dst + idx * 8, m);
+}
+
+// global average pool: block per image, thread per 8-channel group, fp32 accumulation in pixel order
+template <typename T>
+__global__ void gap_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int HW, int C8) {
+  const int n = blockIdx.x;
+  const T* s = src + static_cast<size_t>(n) * HW * C8 * 8;
+  const float inv = 1.0f / static_cast<float>(HW);
+  for (int g = threadIdx.x; g < C8; g += blockDim.x) {
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int p = 0; p < HW; ++p) {
+      float v[8];
+      Vec8<T>::load(s + (static_cast<size_t>(p) * C8 + g) * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] *= inv;
+    Vec8<T>::store(dst + (static_cast<size_t>(n) * C8 + g) * 8, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// depthwise conv + folded BN + activation (+ residual), NHWC, 8 channels per thread
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void dwconv_nhwc_kernel(const T* __restrict__ src, const T* __restrict__ w_rsc, T* __restrict__ dst,
+                                   const float* __restrict__ scale, const float* __restrict__ shift,
+                                   const T* __restrict__ residual, int H, int W, int C8, int P, int Q, int R, int S,
+                                   int stride, int pad, int act1, float alpha1, int act2, float alpha2, size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % C8);
+  size_t t = idx / C8;
+  const int q = static_cast<int>(t % Q);
+  t /= Q;
+  const int pp = static_cast<int>(t % P);
+  const size_t n = t / P;
+  const int C = C8 * 8;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  const int h0 = pp * stride - pad, w0 = q * stride - pad;
+  for (int r = 0; r < R; ++r) {
+    const int h = h0 + r;
+    if (h < 0 || h >= H) continue;
+    for (int s = 0; s < S; ++s) {
+      const int w = w0 + s;
+      if (w < 0 || w >= W) continue;
+      float v[8], k[8];
+      Vec8<T>::load(src + ((n * H + h) * W + w) * static_cast<size_t>(C) + c8 * 8, v);
+      Vec8<T>::load(w_rsc + static_cast<size_t>(r * S + s) * C + c8 * 8, k);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(v[i], k[i], acc[i]);
+    }
+  }
+  float res[8];
+  if (residual) Vec8<T>::load(residual + idx * 8, res);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    float y = apply_act(fmaf(acc[i], __ldg(scale + c8 * 8 + i), __ldg(shift + c8 * 8 + i)), act1, alpha1);
+    if (residual) y += res[i];
+    acc[i] = apply_act(y, act2, alpha2);
+  }
+  Vec8<T>::store(dst + idx * 8, acc);
+}
+
+template <typename T>
+__global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ dst, size_t n8, int act,
+                               float alpha) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= n8) return;
+  float x[8], y[8];
+  Vec8<T>::load(a + idx * 8, x);
+  if (b) {
+    Vec8<T>::load(b + idx * 8, y);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] += y[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = apply_act(x[i], act, alpha);
+  Vec8<T>::store(dst + idx * 8, x);
+}
+
+// one warp per row; first maximal index wins (torch.argmax on ties returns the first occurrence)
+__global__ void argmax_rows_kernel(const float* __restrict__ logits, long long* __restrict__ dst, int N, int K) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* p = logits + static_cast<size_t>(row) * K;
+  float best = -FLT_MAX;
+  int besti = 0x7fffffff;
+  for (int i = lane; i < K; i += 32) {
+    const float v = p[i];
+    if (v > best) best = v, besti = i;
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oi = __shfl_xor_sync(0xffffffffu, besti, off);
+    if (ob > best || (ob == best && oi < besti)) best = ob, besti = oi;
+  }
+  if (lane == 0) dst[row] = besti;
+}
+
+// ------------------------------------------------------------------------------------------------
+// fp32 direct convolution (validation mode): thread = (pixel, 4 output channels)
+// weights [R][S][C/g][K]; lanes run along K so weight loads coalesce and input loads broadcast
+// ------------------------------------------------------------------------------------------------
+__global__ void conv_direct_f32_kernel(const float* __restrict__ in, const float* __restrict__ w, float* __restrict__ out,
+                                       const float* __restrict__ scale, const float* __restrict__ shift,
+                                       const float* __restrict__ residual, int H, int W, int C, int Cs, int P, int Q,
+                                       int K, int R, int S, int stride, int pad, int dil, int groups, int act1,
+                                       float alpha1, int act2, float alpha2, size_t total) {
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int k = static_cast<int>(idx % K);
+  size_t t = idx / K;
+  const int q = static_cast<int>(t % Q);
+  t /= Q;
+  const int pp = static_cast<int>(t % P);
+  const size_t n = t / P;
+  const int Cg = C / groups, Kg = K / groups;
+  const int cbeg = (k / Kg) * Cg;
+  float acc = 0.0f;
+  const int h0 = pp * stride - pad, w0 = q * stride - pad;
+  for (int r = 0; r < R; ++r) {
+    const int h = h0 + r * dil;
+    if (h < 0 || h >= H) continue;
+    for (int s = 0; s < S; ++s) {
+      const int ww = w0 + s * dil;
+      if (ww < 0 || ww >= W) continue;
+      const float* ip = in + ((n * H + h) * W + ww) * static_cast<size_t>(Cs) + cbeg;
+      const float* wp = w + (static_cast<size_t>(r * S + s) * Cg) * K + k;
+      for (int c = 0; c < Cg; ++c) acc = fmaf(__ldg(ip + c), __ldg(wp + static_cast<size_t>(c) * K), acc);
+    }
+  }
+  float y = apply_act(fmaf(acc, scale[k], shift[k]), act1, alpha1);
+  if (residual) y += residual[idx];
+  out[idx] = apply_act(y, act2, alpha2);
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// launchers
+// ------------------------------------------------------------------------------------------------
+cudaError_t pack_conv_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cout_pad, int Cin, int R, int S,
+                              int groups, int mode, int Ktot, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(Cout_pad) * Ktot;
+  pack_conv_weights_kernel<<<blocks_for(total), kThreads, 0, st>>>(oihw, dst, Cout, Cout_pad, Cin, R, S, groups, mode, Ktot);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_linear_weights(const float* w, __nv_bfloat16* dst, int F, int Kout, int Kout_pad, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(Kout_pad) * F;
+  pack_linear_weights_kernel<<<blocks_for(total), kThreads, 0, st>>>(w, dst, F, Kout, Kout_pad);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_conv_weights_f32(const float* oihw, float* dst, int Cout, int Cg, int R, int S, cudaStream_t st) {
+  const size_t total = static_cast<size_t>(Cout) * Cg * R * S;
+  pack_conv_weights_f32_kernel<<<blocks_for(total), kThreads, 0, st>>>(oihw, dst, Cout, Cg, R, S);
+  return cudaGetLastError();
+}
+
+cudaError_t pack_dw_weights(const float* oihw, void* dst, int C, int RS, int is_f32, cudaStream_t st) {
+  const int total = C * RS;
+  if (is_f32)
+    pack_dw_weights_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(oihw, static_cast<float*>(dst), C, RS);
+  else
+    pack_dw_weights_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(oihw, static_cast<__nv_bfloat16*>(dst), C, RS);
+  return cudaGetLastError();
+}
+
+cudaError_t fold_bn(float* scale, float* shift, const float* gamma, const float* beta, const float* mean,
+                    const float* var, const float* bias, float eps, int K, int K_pad, cudaStream_t st) {
+  fold_bn_kernel<<<blocks_for(K_pad), kThreads, 0, st>>>(scale, shift, gamma, beta, mean, var, bias, eps, K, K_pad);
+  return cudaGetLastError();
+}
+
+cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W, int Cs, int is_f32, cudaStream_t st) {
+  const size_t HW = static_cast<size_t>(H) * W;
+  if (C <= 4 && Cs == 4) {
+    const size_t total = static_cast<size_t>(N) * HW;
+    if (is_f32)
+      import_nchw_smallc_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(src, static_cast<float*>(dst), C, HW, total);
+    else
+      import_nchw_smallc_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), C, HW, total);
+    return cudaGetLastError();
+  }
+  if (Cs != C) return cudaErrorInvalidValue;
+  dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
+  if (is_f32)
+    import_nchw_tile_kernel<float><<<grid, block, 0, st>>>(src, static_cast<float*>(dst), C, static_cast<int>(HW));
+  else
+    import_nchw_tile_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), C, static_cast<int>(HW));
+  return cudaGetLastError();
+}
+
+cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W, int is_f32, cudaStream_t st) {
+  const int HW = H * W;
+  dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
+  if (is_f32)
+    export_nchw_tile_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(src), dst, C, HW);
+  else
+    export_nchw_tile_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst, C, HW);
+  return cudaGetLastError();
+}
+
+cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad,
+                         int is_f32, cudaStream_t st) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
+  if (is_f32)
+    maxpool_nhwc_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+  else
+    maxpool_nhwc_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+  return cudaGetLastError();
+}
+
+cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const int threads = C / 8 >= 256 ? 256 : (C / 8 >= 128 ? 128 : 64);
+  if (is_f32)
+    gap_nhwc_kernel<float><<<N, threads, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), HW, C / 8);
+  else
+    gap_nhwc_kernel<__nv_bfloat16><<<N, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), HW, C / 8);
+  return cudaGetLastError();
+}
+
+cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const float* scale, const float* shift,
+                        const void* residual, int N, int H, int W, int C, int P, int Q, int R, int S, int stride, int pad,
+                        int act1, float alpha1, int act2, float alpha2, int is_f32, cudaStream_t st) {
+  if (C % 8) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
+  if (is_f32)
+    dwconv_nhwc_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(
+        static_cast<const float*>(src), static_cast<const float*>(w_rsc), static_cast<float*>(dst), scale, shift,
+        static_cast<const float*>(residual), H, W, C / 8, P, Q, R, S, stride, pad, act1, alpha1, act2, alpha2, total);
+  else
+    dwconv_nhwc_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(
+        static_cast<const __nv_bfloat16*>(src), static_cast<const __nv_bfloat16*>(w_rsc),
+        static_cast<__nv_bfloat16*>(dst), scale, shift, static_cast<const __nv_bfloat16*>(residual), H, W, C / 8, P, Q,
+        R, S, stride, pad, act1, alpha1, act2, alpha2, total);
+  return cudaGetLastError();
+}
+
+cudaError_t add_act(const void* a, const void* b, void* dst, size_t n, int act, float alpha, int is_f32, cudaStream_t st) {
+  if (n % 8) return cudaErrorInvalidValue;
+  const size_t n8 = n / 8;
+  if (is_f32)
+    add_act_kernel<float><<<blocks_for(n8), kThreads, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(dst), n8, act, alpha);
+  else
+    add_act_kernel<__nv_bfloat16><<<blocks_for(n8), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(dst), n8, act, alpha);
+  return cudaGetLastError();
+}
+
+cudaError_t argmax_rows(const float* logits, long long* dst, int N, int K, cudaStream_t st) {
+  const int warps_per_block = 8;
+  argmax_rows_kernel<<<(N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(logits, dst, N, K);
+  return cudaGetLastError();
+}
+
+cudaError_t conv_direct_f32(const float* in, const float* w_rsck, float* out, const float* scale, const float* shift,
+                            const float* residual, int N, int H, int W, int C, int P, int Q, int K, int R, int S,
+                            int stride, int pad, int dil, int groups, int act1, float alpha1, int act2, float alpha2,
+                            cudaStream_t st) {
+  const size_t total = static_cast<size_t>(N) * P * Q * K;
+  const int Cs = C <= 4 ? 4 : C;  // stems read the NHWC4 import
+  conv_direct_f32_kernel<<<blocks_for(total), kThreads, 0, st>>>(in, w_rsck, out, scale, shift, residual, H, W, C, Cs, P,
+                                                                  Q, K, R, S, stride, pad, dil, groups, act1, alpha1,
+                                                                  act2, alpha2, total);
+  return cudaGetLastError();
+}
+
+}  // namespace tlxcv

@@ -1,0 +1,93 @@
+// Host-side declarations of the kernel launchers (internal to libtlxcv_b200.so).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/tlxcv_b200.h"
+
+namespace tlxcv {
+
+// ---- implicit-GEMM conv on tcgen05 -------------------------------------------------------------
+enum ConvMode : int {
+  kModeTiled = 0,   // 1x1 stride-1: A = [M][C] plain 2-D TMA tiles
+  kModeIm2col = 1,  // general RxS / stride / pad: A tiles by im2col-mode TMA from NHWC
+  kModeGatherC4 = 2 // C_in <= 4 stems: producer warps gather from NHWC4 into the swizzled A tile
+};
+
+struct ConvKernelParams {
+  int M, Cout;
+  int num_kb;      // 64-wide K blocks per output tile
+  int kb_per_tap;  // K blocks per filter tap (ceil(Cin/64)); taps = num_kb / kb_per_tap
+  int S;           // filter width (tap -> (r, s))
+  int P, Q, H, W;  // output / input spatial size
+  int stride, pad, dil;
+  int m_tiles, n_tiles;
+  int a_chan_from_n;  // grouped conv with 64-channel block-diagonal weights: A channel base = n_tile * 64
+  // epilogue: y = act2(act1(acc * scale + shift) + residual)
+  const float* scale;
+  const float* shift;
+  const __nv_bfloat16* residual;
+  void* out;
+  int act1;
+  float alpha1;
+  int act2;
+  float alpha2;
+  int out_f32;
+  // gather mode
+  const __nv_bfloat16* in_c4;
+  int R, KR;  // filter height; K elements reserved per filter row (16 or 32)
+};
+
+struct TcConvLaunch {
+  CUtensorMap tmapA, tmapB;
+  ConvKernelParams p;
+  int mode, block_n, grid, threads, smem;
+};
+
+// Encodes the TMA descriptors and picks tile shape; returns an empty string or an error message.
+std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
+                            int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
+                            int pad, int dil, int groups, int force_block_n);
+cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
+cudaError_t tc_conv_set_attributes();
+// number of K elements per output channel in the packed weight matrix for this geometry
+int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode);
+int tc_conv_mode(int Cin, int R, int S, int stride, int pad, int groups);
+
+// ---- weight / BN preparation -------------------------------------------------------------------
+// OIHW fp32 -> [Cout_pad][Ktot] bf16 in the K order the conv kernel consumes.
+cudaError_t pack_conv_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cout_pad, int Cin, int R, int S,
+                              int groups, int mode, int Ktot, cudaStream_t st);
+// (in,out) fp32 -> [Kout_pad][F] bf16
+cudaError_t pack_linear_weights(const float* w_in_out, __nv_bfloat16* dst, int F, int Kout, int Kout_pad, cudaStream_t st);
+// OIHW fp32 -> [R][S][C/g][K] fp32 (validation path) ; (in,out) linear is already [F][K]
+cudaError_t pack_conv_weights_f32(const float* oihw, float* dst, int Cout, int Cg, int R, int S, cudaStream_t st);
+// depthwise: OIHW [C][1][R][S] -> [R*S][C] (T = bf16 or fp32)
+cudaError_t pack_dw_weights(const float* oihw, void* dst, int C, int RS, int is_f32, cudaStream_t st);
+// scale = gamma / sqrt(var + eps), shift = beta + (bias - mean) * scale   (any pointer may be NULL)
+cudaError_t fold_bn(float* scale, float* shift, const float* gamma, const float* beta, const float* mean,
+                    const float* var, const float* bias, float eps, int K, int K_pad, cudaStream_t st);
+
+// ---- memory-bound kernels (T = __nv_bfloat16 or float, is_f32 selects) -------------------------
+cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W, int Cs, int is_f32, cudaStream_t st);
+cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W, int is_f32, cudaStream_t st);
+cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad,
+                         int is_f32, cudaStream_t st);
+cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st);
+cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const float* scale, const float* shift,
+                        const void* residual, int N, int H, int W, int C, int P, int Q, int R, int S, int stride, int pad,
+                        int act1, float alpha1, int act2, float alpha2, int is_f32, cudaStream_t st);
+cudaError_t add_act(const void* a, const void* b, void* dst, size_t n, int act, float alpha, int is_f32, cudaStream_t st);
+cudaError_t argmax_rows(const float* logits, long long* dst, int N, int K, cudaStream_t st);
+// fp32 direct conv on CUDA cores (validation mode; dense, grouped and depthwise)
+cudaError_t conv_direct_f32(const float* in, const float* w_rsck, float* out, const float* scale, const float* shift,
+                            const float* residual, int N, int H, int W, int C, int P, int Q, int K, int R, int S,
+                            int stride, int pad, int dil, int groups, int act1, float alpha1, int act2, float alpha2,
+                            cudaStream_t st);
+
+}  // namespace tlxcv

@@ -1,0 +1,643 @@
+// C ABI of libtlxcv_b200.so (include/tlxcv_b200.h): context, plan build (workspace planning,
+// weight packing, BN folding, kernel/tile selection, TMA descriptors), plan run (stream launch or
+// CUDA-graph replay), host-buffer run, per-op profiling.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "kernels.h"
+
+using namespace tlxcv;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct TensorRt {
+  tlxcv_tensor_desc d;
+  int cs = 0;          // storage channels (NHWC4 for C<=4 activations)
+  size_t bytes = 0;
+  size_t offset = 0;   // into the arena (internal tensors)
+  int ext_index = -1;  // position among inputs / outputs (external tensors)
+  int first_def = -1, last_use = -1;
+};
+
+enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax };
+
+struct OpRt {
+  tlxcv_op_desc d;
+  int impl = 0;
+  TcConvLaunch tc;            // kImplTcConv
+  void* weights = nullptr;    // packed weights (owned)
+  float* scale = nullptr;     // folded BN / bias (owned)
+  float* shift = nullptr;
+  tlxcv_op_info info;
+};
+
+}  // namespace
+
+struct tlxcv_ctx {
+  int device = 0;
+  int sm_count = 0;
+  std::string error;
+};
+
+struct tlxcv_plan {
+  tlxcv_ctx* ctx = nullptr;
+  int precision = 0;
+  bool f32 = false;
+  size_t esize = 2;
+  std::vector<TensorRt> tensors;
+  std::vector<OpRt> ops;
+  std::vector<int> input_ids, output_ids;
+  uint8_t* arena = nullptr;
+  size_t arena_bytes = 0;
+  std::vector<void*> owned;
+  // CUDA graph cache (one entry: same external pointers => replay)
+  cudaGraphExec_t graph_exec = nullptr;
+  std::vector<const void*> graph_key;
+  // host-run staging
+  std::vector<void*> stage_in, stage_out;
+};
+
+namespace {
+
+int fail(tlxcv_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx)
+    ctx->error = buf;
+  else
+    g_create_error = buf;
+  return code;
+}
+
+#define TLX_CUDA(ctx, expr)                                                                              \
+  do {                                                                                                   \
+    cudaError_t _e = (expr);                                                                             \
+    if (_e != cudaSuccess)                                                                               \
+      return fail(ctx, _e == cudaErrorMemoryAllocation ? TLXCV_ERR_OOM : TLXCV_ERR_CUDA, "%s failed: %s", \
+                  #expr, cudaGetErrorString(_e));                                                        \
+  } while (0)
+
+size_t dtype_size(const tlxcv_plan* p, int dt) {
+  switch (dt) {
+    case TLXCV_F32: return 4;
+    case TLXCV_BF16: return 2;
+    case TLXCV_I64: return 8;
+    default: return p->esize;
+  }
+}
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// first-fit arena with coalescing free list
+struct Arena {
+  std::map<size_t, size_t> free_blocks;  // offset -> size
+  size_t end = 0;
+  size_t alloc(size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    for (auto it = free_blocks.begin(); it != free_blocks.end(); ++it) {
+      if (it->second >= bytes) {
+        size_t off = it->first, rest = it->second - bytes;
+        free_blocks.erase(it);
+        if (rest) free_blocks[off + bytes] = rest;
+        return off;
+      }
+    }
+    // extend a trailing free block if there is one
+    if (!free_blocks.empty()) {
+      auto last = std::prev(free_blocks.end());
+      if (last->first + last->second == end) {
+        size_t off = last->first;
+        free_blocks.erase(last);
+        end = off + bytes;
+        return off;
+      }
+    }
+    size_t off = end;
+    end += bytes;
+    return off;
+  }
+  void release(size_t off, size_t bytes) {
+    bytes = align_up(bytes, 1024);
+    auto it = free_blocks.emplace(off, bytes).first;
+    auto nxt = std::next(it);
+    if (nxt != free_blocks.end() && it->first + it->second == nxt->first) {
+      it->second += nxt->second;
+      free_blocks.erase(nxt);
+    }
+    if (it != free_blocks.begin()) {
+      auto prv = std::prev(it);
+      if (prv->first + prv->second == it->first) {
+        prv->second += it->second;
+        free_blocks.erase(it);
+      }
+    }
+  }
+};
+
+void* tensor_ptr(const tlxcv_plan* p, int t, const void* const* inputs, void* const* outputs) {
+  const TensorRt& T = p->tensors[t];
+  if (T.d.role == TLXCV_ROLE_INPUT) return const_cast<void*>(inputs[T.ext_index]);
+  if (T.d.role == TLXCV_ROLE_OUTPUT) return outputs[T.ext_index];
+  return p->arena + T.offset;
+}
+
+template <typename T>
+int dev_alloc(tlxcv_plan* p, T** out, size_t count) {
+  void* ptr = nullptr;
+  cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(count * sizeof(T), 256));
+  if (e != cudaSuccess) return fail(p->ctx, TLXCV_ERR_OOM, "cudaMalloc(%zu) failed: %s", count * sizeof(T), cudaGetErrorString(e));
+  p->owned.push_back(ptr);
+  *out = static_cast<T*>(ptr);
+  return TLXCV_OK;
+}
+
+void set_info(OpRt& op, const char* kernel, int launches, int bound, double flops, double bytes, int grid, int block,
+              int smem, int tile_n) {
+  memset(&op.info, 0, sizeof op.info);
+  snprintf(op.info.kernel, sizeof op.info.kernel, "%s", kernel);
+  op.info.launches = launches, op.info.bound = bound, op.info.flops = flops, op.info.bytes = bytes;
+  op.info.grid = grid, op.info.block = block, op.info.smem_bytes = smem, op.info.tile_n = tile_n;
+}
+
+int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
+  tlxcv_ctx* ctx = p->ctx;
+  const tlxcv_op_desc& d = op.d;
+  const TensorRt& in = p->tensors[d.in0];
+  const TensorRt& out = p->tensors[d.out];
+  const int N = in.d.n, H = in.d.h, W = in.d.w, C = in.d.c, K = out.d.c;
+  const int R = is_linear ? 1 : d.r, S = is_linear ? 1 : d.s;
+  const int stride = is_linear ? 1 : d.stride, pad = is_linear ? 0 : d.pad, dil = is_linear ? 1 : d.dil;
+  const int groups = is_linear ? 1 : d.groups;
+  if (!d.filters) return fail(ctx, TLXCV_ERR_INVALID, "op %s: filters pointer is NULL", is_linear ? "linear" : "conv");
+  if (groups < 1 || C % groups || K % groups) return fail(ctx, TLXCV_ERR_INVALID, "conv: channels not divisible by groups");
+  const int P = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1, Q = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  if (P != out.d.h || Q != out.d.w || out.d.n != N)
+    return fail(ctx, TLXCV_ERR_INVALID, "conv: output tensor is %dx%dx%d but geometry gives %dx%dx%d", out.d.n, out.d.h,
+                out.d.w, N, P, Q);
+  if (d.in1 >= 0) {
+    const TensorRt& r = p->tensors[d.in1];
+    if (r.d.n != out.d.n || r.d.h != out.d.h || r.d.w != out.d.w || r.d.c != out.d.c)
+      return fail(ctx, TLXCV_ERR_INVALID, "conv: residual shape mismatch");
+  }
+  const int Cg = C / groups;
+  const int K_pad = static_cast<int>(align_up(K, 256));
+  int rc;
+  if ((rc = dev_alloc(p, &op.scale, K_pad)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.shift, K_pad)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, fold_bn(op.scale, op.shift, d.bn_gamma, d.bn_beta, d.bn_mean, d.bn_var, d.bias, d.bn_eps, K, K_pad, st));
+
+  const double M = static_cast<double>(N) * P * Q;
+  const double flops = 2.0 * M * K * Cg * R * S;
+  const double wbytes = static_cast<double>(K) * Cg * R * S * (p->f32 ? 4 : 2);
+  const double obytes = M * K * (out.d.dtype == TLXCV_F32 ? 4 : p->esize);
+  const double bytes = static_cast<double>(N) * H * W * C * p->esize + wbytes + obytes + (d.in1 >= 0 ? M * K * p->esize : 0);
+
+  if (p->f32) {
+    float* w = nullptr;
+    if (is_linear) {
+      // (in,out) == [R=1][S=1][F][K] already: plain copy so that the plan owns its parameters
+      if ((rc = dev_alloc(p, &w, static_cast<size_t>(K) * C)) != TLXCV_OK) return rc;
+      TLX_CUDA(ctx, cudaMemcpyAsync(w, d.filters, static_cast<size_t>(K) * C * sizeof(float), cudaMemcpyDeviceToDevice, st));
+      op.weights = w;
+    } else {
+      if ((rc = dev_alloc(p, &w, static_cast<size_t>(K) * Cg * R * S)) != TLXCV_OK) return rc;
+      TLX_CUDA(ctx, pack_conv_weights_f32(d.filters, w, K, Cg, R, S, st));
+      op.weights = w;
+    }
+    op.impl = kImplDirectF32;
+    set_info(op, "conv_direct_f32", 1, 1, flops, bytes, 0, 256, 0, 0);
+    return TLXCV_OK;
+  }
+  const bool depthwise = !is_linear && groups == C && K == C && groups > 1;
+  if (depthwise) {
+    if (dil != 1) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "depthwise conv: dilation must be 1");
+    __nv_bfloat16* w = nullptr;
+    if ((rc = dev_alloc(p, &w, static_cast<size_t>(C) * R * S)) != TLXCV_OK) return rc;
+    TLX_CUDA(ctx, pack_dw_weights(d.filters, w, C, R * S, 0, st));
+    op.weights = w;
+    op.impl = kImplDwConv;
+    set_info(op, "dwconv_nhwc_bf16", 1, 0, flops, bytes, 0, 256, 0, 0);
+    return TLXCV_OK;
+  }
+  // tensor-core path
+  const int mode = tc_conv_mode(C, R, S, stride, pad, groups);
+  const int Ktot = tc_conv_packed_k(C, R, S, groups, mode);
+  __nv_bfloat16* w = nullptr;
+  if ((rc = dev_alloc(p, &w, static_cast<size_t>(K_pad) * Ktot)) != TLXCV_OK) return rc;
+  if (is_linear)
+    TLX_CUDA(ctx, pack_linear_weights(d.filters, w, C, K, K_pad, st));
+  else
+    TLX_CUDA(ctx, pack_conv_weights(d.filters, w, K, K_pad, C, R, S, groups, mode, Ktot, st));
+  if (is_linear && Ktot != C)
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "linear: in_features (%d) must be a multiple of 64", C);
+  op.weights = w;
+  const __nv_bfloat16* act_in = reinterpret_cast<const __nv_bfloat16*>(p->arena + in.offset);
+  int force_bn = 0;
+  if (const char* e = getenv("TLXCV_FORCE_BLOCK_N")) force_bn = atoi(e);
+  std::string err = tc_conv_prepare(op.tc, ctx->sm_count, act_in, N, H, W, C, in.cs, w, Ktot, K, R, S, stride, pad, dil,
+                                    groups, force_bn);
+  if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
+  ConvKernelParams& kp = op.tc.p;
+  kp.scale = op.scale, kp.shift = op.shift;
+  kp.act1 = d.act1, kp.alpha1 = d.alpha1, kp.act2 = d.act2, kp.alpha2 = d.alpha2;
+  kp.out_f32 = out.d.dtype == TLXCV_F32;
+  if (kp.out_f32 && (K % 4)) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "fp32 conv output needs C_out %% 4 == 0");
+  op.impl = kImplTcConv;
+  char name[48];
+  static const char* mnames[] = {"tiled", "im2col", "gatherc4"};
+  snprintf(name, sizeof name, "conv_tcgen05_%s_n%d%s", mnames[op.tc.mode], op.tc.block_n, groups > 1 ? "_grouped" : "");
+  // tensor-bound when arithmetic intensity exceeds the ridge (~248 FLOP/B on the measured peaks)
+  set_info(op, name, 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.tc.grid, op.tc.threads, op.tc.smem, op.tc.block_n);
+  return TLXCV_OK;
+}
+
+int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* outputs, cudaStream_t st) {
+  tlxcv_ctx* ctx = p->ctx;
+  const tlxcv_op_desc& d = op.d;
+  const TensorRt& in = p->tensors[d.in0];
+  const TensorRt& out = p->tensors[d.out];
+  void* pin = tensor_ptr(p, d.in0, inputs, outputs);
+  void* pout = tensor_ptr(p, d.out, inputs, outputs);
+  void* pres = d.in1 >= 0 ? tensor_ptr(p, d.in1, inputs, outputs) : nullptr;
+  if (!pin || !pout) return fail(ctx, TLXCV_ERR_INVALID, "NULL external tensor pointer");
+  const int is_f32 = p->f32 ? 1 : 0;
+  switch (op.impl) {
+    case kImplImport:
+      TLX_CUDA(ctx, import_nchw(static_cast<const float*>(pin), pout, in.d.n, in.d.c, in.d.h, in.d.w, out.cs, is_f32, st));
+      break;
+    case kImplExport:
+      TLX_CUDA(ctx, export_nchw(pin, static_cast<float*>(pout), in.d.n, in.d.c, in.d.h, in.d.w, is_f32, st));
+      break;
+    case kImplTcConv: {
+      TcConvLaunch L = op.tc;
+      L.p.out = pout;
+      L.p.residual = static_cast<const __nv_bfloat16*>(pres);
+      TLX_CUDA(ctx, tc_conv_launch(L, st));
+      break;
+    }
+    case kImplDwConv:
+      TLX_CUDA(ctx, dwconv_nhwc(pin, op.weights, pout, op.scale, op.shift, pres, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h,
+                                out.d.w, d.r, d.s, d.stride, d.pad, d.act1, d.alpha1, d.act2, d.alpha2, is_f32, st));
+      break;
+    case kImplDirectF32: {
+      const bool lin = d.kind == TLXCV_OP_LINEAR;
+      TLX_CUDA(ctx, conv_direct_f32(static_cast<const float*>(pin), static_cast<const float*>(op.weights),
+                                    static_cast<float*>(pout), op.scale, op.shift, static_cast<const float*>(pres),
+                                    in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, out.d.c, lin ? 1 : d.r, lin ? 1 : d.s,
+                                    lin ? 1 : d.stride, lin ? 0 : d.pad, lin ? 1 : d.dil, lin ? 1 : d.groups, d.act1,
+                                    d.alpha1, d.act2, d.alpha2, st));
+      break;
+    }
+    case kImplMaxpool:
+      TLX_CUDA(ctx, maxpool_nhwc(pin, pout, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, d.r, d.stride, d.pad, is_f32, st));
+      break;
+    case kImplGap:
+      TLX_CUDA(ctx, gap_nhwc(pin, pout, in.d.n, in.d.h * in.d.w, in.d.c, is_f32, st));
+      break;
+    case kImplAddAct:
+      TLX_CUDA(ctx, add_act(pin, pres, pout, static_cast<size_t>(in.d.n) * in.d.h * in.d.w * in.d.c, d.act2, d.alpha2, is_f32, st));
+      break;
+    case kImplArgmax:
+      TLX_CUDA(ctx, argmax_rows(static_cast<const float*>(pin), static_cast<long long*>(pout), in.d.n, in.d.c, st));
+      break;
+    default:
+      return fail(ctx, TLXCV_ERR_INVALID, "unknown op implementation");
+  }
+  return TLXCV_OK;
+}
+
+int launch_all(tlxcv_plan* p, const void* const* inputs, void* const* outputs, cudaStream_t st) {
+  for (OpRt& op : p->ops) {
+    int rc = launch_op(p, op, inputs, outputs, st);
+    if (rc != TLXCV_OK) return rc;
+  }
+  return TLXCV_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+extern "C" {
+
+int tlxcv_abi_version(void) { return TLXCV_ABI_VERSION; }
+
+int tlxcv_create(int device, tlxcv_ctx** out) {
+  if (!out) return fail(nullptr, TLXCV_ERR_INVALID, "tlxcv_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0)
+    return fail(nullptr, TLXCV_ERR_NO_DEVICE, "no CUDA device: tlxcv_b200 has no CPU fallback");
+  if (device < 0 || device >= count) return fail(nullptr, TLXCV_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaGetDeviceProperties failed");
+  if (prop.major != 10)
+    return fail(nullptr, TLXCV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a (Blackwell B200) code only",
+                device, prop.major, prop.minor);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaSetDevice failed");
+  cudaError_t e = tc_conv_set_attributes();
+  if (e != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  tlxcv_ctx* c = new tlxcv_ctx();
+  c->device = device;
+  c->sm_count = prop.multiProcessorCount;
+  *out = c;
+  return TLXCV_OK;
+}
+
+int tlxcv_destroy(tlxcv_ctx* ctx) {
+  delete ctx;
+  return TLXCV_OK;
+}
+
+const char* tlxcv_last_error(const tlxcv_ctx* ctx) { return ctx ? ctx->error.c_str() : g_create_error.c_str(); }
+
+int tlxcv_device_sm_count(const tlxcv_ctx* ctx) { return ctx ? ctx->sm_count : 0; }
+
+int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_tensors, const tlxcv_op_desc* ops, int n_ops,
+                     int precision, void* stream, tlxcv_plan** out) {
+  if (!ctx) return TLXCV_ERR_INVALID;
+  if (!tensors || !ops || !out || n_tensors <= 0 || n_ops <= 0) return fail(ctx, TLXCV_ERR_INVALID, "plan_build: bad arguments");
+  if (precision != TLXCV_PREC_BF16 && precision != TLXCV_PREC_F32_VALIDATE)
+    return fail(ctx, TLXCV_ERR_INVALID, "plan_build: unknown precision %d", precision);
+  *out = nullptr;
+  TLX_CUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  tlxcv_plan* p = new tlxcv_plan();
+  p->ctx = ctx;
+  p->precision = precision;
+  p->f32 = precision == TLXCV_PREC_F32_VALIDATE;
+  p->esize = p->f32 ? 4 : 2;
+  struct Guard {
+    tlxcv_plan* p;
+    ~Guard() {
+      if (p) tlxcv_plan_destroy(p);
+    }
+  } guard{p};
+
+  // ---- tensors ----
+  p->tensors.resize(n_tensors);
+  for (int i = 0; i < n_tensors; ++i) {
+    TensorRt& T = p->tensors[i];
+    T.d = tensors[i];
+    if (T.d.n <= 0 || T.d.h <= 0 || T.d.w <= 0 || T.d.c <= 0) return fail(ctx, TLXCV_ERR_INVALID, "tensor %d: non-positive dimension", i);
+    T.cs = T.d.c;
+    if (T.d.dtype == TLXCV_ACT && T.d.role == TLXCV_ROLE_INTERNAL) {
+      if (T.d.c <= 4)
+        T.cs = 4;
+      else if (T.d.c % 8)
+        return fail(ctx, TLXCV_ERR_UNSUPPORTED, "tensor %d: activation channels (%d) must be <= 4 or a multiple of 8", i, T.d.c);
+    }
+    T.bytes = static_cast<size_t>(T.d.n) * T.d.h * T.d.w * T.cs * dtype_size(p, T.d.dtype);
+    if (T.d.role == TLXCV_ROLE_INPUT) {
+      T.ext_index = static_cast<int>(p->input_ids.size());
+      p->input_ids.push_back(i);
+    } else if (T.d.role == TLXCV_ROLE_OUTPUT) {
+      T.ext_index = static_cast<int>(p->output_ids.size());
+      p->output_ids.push_back(i);
+    }
+  }
+  // ---- ops: validate indices, liveness ----
+  p->ops.resize(n_ops);
+  for (int i = 0; i < n_ops; ++i) {
+    OpRt& op = p->ops[i];
+    op.d = ops[i];
+    const tlxcv_op_desc& d = op.d;
+    if (d.in0 < 0 || d.in0 >= n_tensors || d.out < 0 || d.out >= n_tensors || d.in1 >= n_tensors)
+      return fail(ctx, TLXCV_ERR_INVALID, "op %d: tensor index out of range", i);
+    for (int t : {d.in0, d.in1}) {
+      if (t < 0) continue;
+      if (p->tensors[t].d.role != TLXCV_ROLE_INPUT && p->tensors[t].first_def < 0)
+        return fail(ctx, TLXCV_ERR_INVALID, "op %d reads tensor %d before it is produced", i, t);
+      p->tensors[t].last_use = i;
+    }
+    if (p->tensors[d.out].first_def >= 0 || p->tensors[d.out].d.role == TLXCV_ROLE_INPUT)
+      return fail(ctx, TLXCV_ERR_INVALID, "op %d: tensor %d is written twice", i, d.out);
+    p->tensors[d.out].first_def = i;
+    p->tensors[d.out].last_use = std::max(p->tensors[d.out].last_use, i);
+  }
+  // ---- workspace: first-fit arena over tensor lifetimes ----
+  {
+    Arena arena;
+    const bool no_reuse = getenv("TLXCV_NO_REUSE") != nullptr;  // debugging: keep every intermediate readable
+    for (int i = 0; i < n_ops; ++i) {
+      TensorRt& o = p->tensors[p->ops[i].d.out];
+      if (o.d.role == TLXCV_ROLE_INTERNAL) o.offset = arena.alloc(o.bytes);
+      for (int t : {p->ops[i].d.in0, p->ops[i].d.in1, p->ops[i].d.out}) {
+        if (t < 0) continue;
+        TensorRt& T = p->tensors[t];
+        if (!no_reuse && T.d.role == TLXCV_ROLE_INTERNAL && T.last_use == i && T.first_def >= 0) {
+          arena.release(T.offset, T.bytes);
+          T.last_use = -2;  // released
+        }
+      }
+    }
+    p->arena_bytes = std::max<size_t>(arena.end, 1024);
+    void* ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, p->arena_bytes);
+    if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_OOM, "workspace cudaMalloc(%zu) failed: %s", p->arena_bytes, cudaGetErrorString(e));
+    p->arena = static_cast<uint8_t*>(ptr);
+  }
+  // ---- compile ops ----
+  for (int i = 0; i < n_ops; ++i) {
+    OpRt& op = p->ops[i];
+    const tlxcv_op_desc& d = op.d;
+    const TensorRt& in = p->tensors[d.in0];
+    const TensorRt& o = p->tensors[d.out];
+    const double in_bytes = static_cast<double>(in.bytes), out_bytes = static_cast<double>(o.bytes);
+    int rc = TLXCV_OK;
+    switch (d.kind) {
+      case TLXCV_OP_IMPORT_NCHW:
+        if (in.d.role != TLXCV_ROLE_INPUT || in.d.dtype != TLXCV_F32 || o.d.dtype != TLXCV_ACT || o.d.role != TLXCV_ROLE_INTERNAL)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: import expects external f32 -> internal activation", i);
+        op.impl = kImplImport;
+        set_info(op, o.cs == 4 ? "import_nchw_c4" : "import_nchw_tile", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_EXPORT_NCHW:
+        if (o.d.role != TLXCV_ROLE_OUTPUT || o.d.dtype != TLXCV_F32 || in.d.dtype != TLXCV_ACT || in.cs != in.d.c)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: export expects internal activation -> external f32", i);
+        op.impl = kImplExport;
+        set_info(op, "export_nchw_tile", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_CONV:
+        if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_ACT) return fail(ctx, TLXCV_ERR_INVALID, "op %d: conv tensors must be activations", i);
+        rc = compile_conv(p, op, st, false);
+        break;
+      case TLXCV_OP_LINEAR:
+        if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_F32 || in.d.h != 1 || in.d.w != 1)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: linear expects (N, F) activation -> (N, K) f32", i);
+        rc = compile_conv(p, op, st, true);
+        break;
+      case TLXCV_OP_MAXPOOL:
+        if (d.r != d.s) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: non-square pooling window", i);
+        if (o.d.h != (in.d.h + 2 * d.pad - d.r) / d.stride + 1 || o.d.w != (in.d.w + 2 * d.pad - d.r) / d.stride + 1 || o.d.c != in.d.c)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: maxpool output shape mismatch", i);
+        op.impl = kImplMaxpool;
+        set_info(op, "maxpool_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_GAP:
+        if (o.d.h != 1 || o.d.w != 1 || o.d.c != in.d.c) return fail(ctx, TLXCV_ERR_INVALID, "op %d: gap output shape mismatch", i);
+        op.impl = kImplGap;
+        set_info(op, "gap_nhwc", 1, 0, 0, in_bytes + out_bytes, in.d.n, 256, 0, 0);
+        break;
+      case TLXCV_OP_ADD_ACT:
+        if (in.cs != in.d.c) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: add/act on a padded-channel tensor", i);
+        op.impl = kImplAddAct;
+        set_info(op, "add_act", 1, 0, 0, in_bytes * (d.in1 >= 0 ? 2 : 1) + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_ARGMAX:
+        if (in.d.dtype != TLXCV_F32 || o.d.dtype != TLXCV_I64) return fail(ctx, TLXCV_ERR_INVALID, "op %d: argmax expects f32 -> i64", i);
+        op.impl = kImplArgmax;
+        set_info(op, "argmax_rows", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      default:
+        return fail(ctx, TLXCV_ERR_INVALID, "op %d: unknown kind %d", i, d.kind);
+    }
+    if (rc != TLXCV_OK) {
+      std::string msg = ctx->error;
+      return fail(ctx, rc, "op %d: %s", i, msg.c_str());
+    }
+  }
+  guard.p = nullptr;
+  *out = p;
+  return TLXCV_OK;
+}
+
+int tlxcv_plan_destroy(tlxcv_plan* p) {
+  if (!p) return TLXCV_OK;
+  cudaSetDevice(p->ctx->device);
+  cudaDeviceSynchronize();
+  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  for (void* q : p->owned) cudaFree(q);
+  for (void* q : p->stage_in) cudaFree(q);
+  for (void* q : p->stage_out) cudaFree(q);
+  if (p->arena) cudaFree(p->arena);
+  delete p;
+  return TLXCV_OK;
+}
+
+int tlxcv_plan_run(tlxcv_plan* p, const void* const* inputs, void* const* outputs, void* stream, int use_graph) {
+  if (!p || !inputs || !outputs) return TLXCV_ERR_INVALID;
+  tlxcv_ctx* ctx = p->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!use_graph) return launch_all(p, inputs, outputs, st);
+  std::vector<const void*> key;
+  for (size_t i = 0; i < p->input_ids.size(); ++i) key.push_back(inputs[i]);
+  for (size_t i = 0; i < p->output_ids.size(); ++i) key.push_back(outputs[i]);
+  if (!p->graph_exec || key != p->graph_key) {
+    if (p->graph_exec) {
+      cudaGraphExecDestroy(p->graph_exec);
+      p->graph_exec = nullptr;
+    }
+    cudaStream_t cap;
+    TLX_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+    cudaGraph_t graph = nullptr;
+    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+    int rc = TLXCV_OK;
+    if (e == cudaSuccess) {
+      rc = launch_all(p, inputs, outputs, cap);
+      e = cudaStreamEndCapture(cap, &graph);
+    }
+    cudaStreamDestroy(cap);
+    if (rc != TLXCV_OK) {
+      if (graph) cudaGraphDestroy(graph);
+      return rc;
+    }
+    if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e != cudaSuccess) {
+      p->graph_exec = nullptr;
+      return fail(ctx, TLXCV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    }
+    p->graph_key = key;
+  }
+  TLX_CUDA(ctx, cudaGraphLaunch(p->graph_exec, st));
+  return TLXCV_OK;
+}
+
+int tlxcv_plan_run_host(tlxcv_plan* p, const void* const* host_inputs, void* const* host_outputs, void* stream, int use_graph) {
+  if (!p || !host_inputs || !host_outputs) return TLXCV_ERR_INVALID;
+  tlxcv_ctx* ctx = p->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (p->stage_in.empty() && p->stage_out.empty()) {
+    for (int t : p->input_ids) {
+      void* q = nullptr;
+      TLX_CUDA(ctx, cudaMalloc(&q, p->tensors[t].bytes));
+      p->stage_in.push_back(q);
+    }
+    for (int t : p->output_ids) {
+      void* q = nullptr;
+      TLX_CUDA(ctx, cudaMalloc(&q, p->tensors[t].bytes));
+      p->stage_out.push_back(q);
+    }
+  }
+  for (size_t i = 0; i < p->input_ids.size(); ++i)
+    TLX_CUDA(ctx, cudaMemcpyAsync(p->stage_in[i], host_inputs[i], p->tensors[p->input_ids[i]].bytes, cudaMemcpyHostToDevice, st));
+  int rc = tlxcv_plan_run(p, p->stage_in.data(), p->stage_out.data(), stream, use_graph);
+  if (rc != TLXCV_OK) return rc;
+  for (size_t i = 0; i < p->output_ids.size(); ++i)
+    TLX_CUDA(ctx, cudaMemcpyAsync(host_outputs[i], p->stage_out[i], p->tensors[p->output_ids[i]].bytes, cudaMemcpyDeviceToHost, st));
+  return TLXCV_OK;
+}
+
+int tlxcv_plan_profile(tlxcv_plan* p, const void* const* inputs, void* const* outputs, void* stream, float* per_op_ms, int n_ops) {
+  if (!p || !per_op_ms || n_ops != static_cast<int>(p->ops.size())) return TLXCV_ERR_INVALID;
+  tlxcv_ctx* ctx = p->ctx;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  std::vector<cudaEvent_t> ev(p->ops.size() + 1);
+  for (auto& e : ev) TLX_CUDA(ctx, cudaEventCreate(&e));
+  TLX_CUDA(ctx, cudaEventRecord(ev[0], st));
+  int rc = TLXCV_OK;
+  for (size_t i = 0; i < p->ops.size() && rc == TLXCV_OK; ++i) {
+    rc = launch_op(p, p->ops[i], inputs, outputs, st);
+    if (rc == TLXCV_OK && cudaEventRecord(ev[i + 1], st) != cudaSuccess) rc = fail(ctx, TLXCV_ERR_CUDA, "cudaEventRecord failed");
+  }
+  if (rc == TLXCV_OK) {
+    cudaError_t e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) rc = fail(ctx, TLXCV_ERR_CUDA, "profile run failed: %s", cudaGetErrorString(e));
+  }
+  if (rc == TLXCV_OK)
+    for (size_t i = 0; i < p->ops.size(); ++i) cudaEventElapsedTime(&per_op_ms[i], ev[i], ev[i + 1]);
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc;
+}
+
+int tlxcv_plan_num_ops(const tlxcv_plan* p) { return p ? static_cast<int>(p->ops.size()) : 0; }
+
+int tlxcv_plan_num_launches(const tlxcv_plan* p) {
+  int n = 0;
+  if (p)
+    for (const OpRt& op : p->ops) n += op.info.launches;
+  return n;
+}
+
+int tlxcv_plan_op_info(const tlxcv_plan* p, int i, tlxcv_op_info* info) {
+  if (!p || !info || i < 0 || i >= static_cast<int>(p->ops.size())) return TLXCV_ERR_INVALID;
+  *info = p->ops[i].info;
+  return TLXCV_OK;
+}
+
+size_t tlxcv_plan_workspace_bytes(const tlxcv_plan* p) { return p ? p->arena_bytes : 0; }
+
+int tlxcv_plan_read_tensor(tlxcv_plan* p, int t, void* dst, size_t dst_bytes, void* stream) {
+  if (!p || t < 0 || t >= static_cast<int>(p->tensors.size()) || !dst) return TLXCV_ERR_INVALID;
+  const TensorRt& T = p->tensors[t];
+  if (T.d.role != TLXCV_ROLE_INTERNAL) return fail(p->ctx, TLXCV_ERR_INVALID, "read_tensor: tensor %d is external", t);
+  if (dst_bytes < T.bytes) return fail(p->ctx, TLXCV_ERR_INVALID, "read_tensor: need %zu bytes", T.bytes);
+  TLX_CUDA(p->ctx, cudaMemcpyAsync(dst, p->arena + T.offset, T.bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
+  return T.cs;
+}
+
+}  // extern "C"
