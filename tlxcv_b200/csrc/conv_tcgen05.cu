@@ -195,7 +195,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         if (p.residual != nullptr) {
           // coalesced read of the 32 x 32 residual block (64 B row segments), transposed through smem
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {  // 4 x (8 rows x 64 B) = this warp's 32 rows
             const int r = (lane >> 2) + 8 * i, q4 = lane & 3;
             const int gr = m0 + r, col = cbase + q4 * 8;
             uint4 val = make_uint4(0, 0, 0, 0);
@@ -243,7 +243,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           __syncwarp();
           __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          for (int i = 0; i < 4; ++i) {
             const int r = (lane >> 2) + 8 * i, q4 = lane & 3;
             const int gr = m0 + r, col = cbase + q4 * 8;
             const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4));

@@ -318,9 +318,17 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
 }
 
 int launch_all(tlxcv_plan* p, const void* const* inputs, void* const* outputs, cudaStream_t st) {
+  static const bool sync_each = getenv("TLXCV_SYNC_EACH_OP") != nullptr;  // debugging: attribute faults to an op
+  int i = 0;
   for (OpRt& op : p->ops) {
     int rc = launch_op(p, op, inputs, outputs, st);
     if (rc != TLXCV_OK) return rc;
+    if (sync_each) {
+      cudaError_t e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess)
+        return fail(p->ctx, TLXCV_ERR_CUDA, "op %d (%s) faulted: %s", i, op.info.kernel, cudaGetErrorString(e));
+    }
+    ++i;
   }
   return TLXCV_OK;
 }

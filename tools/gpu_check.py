@@ -223,7 +223,7 @@ def worker(names):
             ok, info = run_conv_case(c) if c["kind"] == "conv" else run_model_case(c)
             status = "PASS" if ok else "FAIL"
         except Exception as e:  # noqa: BLE001
-            status, info = "ERROR", dict(error=f"{type(e).__name__}: {e}", tb=traceback.format_exc()[-1500:])
+            status, info = "ERROR", dict(error=f"{type(e).__name__}: {e}"[:300], tb=traceback.format_exc()[-400:])
         info["secs"] = round(time.time() - t0, 2)
         print(f"END {nm} {status} {json.dumps(info)}", flush=True)
         if status == "ERROR" and "CUDA" in info.get("error", ""):
