@@ -99,8 +99,12 @@ def test_reference_files_run_unmodified_on_the_product_shim(name, manifests):
 
     @contextlib.contextmanager
     def shim():
+        import sys
+
         with tlx_compat.installed():         # supplies the inert paddle / paddle2tlx stubs two files import
             with tlx.as_tensorlayerx():      # ... and the product takes the tensorlayerx names
+                # mobilenetv2.py:98 takes its Dropout from paddle2tlx; give it the product's
+                sys.modules["paddle2tlx.pd2tlx.ops.tlxops"].tlx_Dropout = nn.Dropout
                 yield
 
     ref_model = ref_loader.build(name, shim=shim)

@@ -32,9 +32,13 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
-constexpr int kStagingBytes = 4 * 2048;         // 4 epilogue warps x (32 rows x 64 B)
+constexpr int kEpiWarps = 8;                    // warps 2..9
+constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
+constexpr int kStagingBytes = kEpiWarps * 4096; // per epilogue warp: 2 x (32 rows x 64 B), SWIZZLE_64B
 constexpr int kBarrierBytes = 256;
 constexpr int kMaxStages = 8;
+constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
+constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 576
 
 template <int BLOCK_N>
 struct Cfg {
@@ -55,10 +59,25 @@ struct PipeState {
   }
 };
 
+// activation applied to a register tile; the switch is outside the element loop
+template <int N>
+__device__ __forceinline__ void act_inplace(float (&f)[N], int act, float alpha) {
+  if (act == TLXCV_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (act == TLXCV_ACT_RELU6) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fminf(fmaxf(f[j], 0.0f), 6.0f);
+  } else if (act == TLXCV_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = f[j] > 0.0f ? f[j] : f[j] * alpha;
+  }
+}
+
 template <int BLOCK_N, int MODE>
-__global__ void __launch_bounds__(MODE == kModeGatherC4 ? 384 : 256, 1)
+__global__ void __launch_bounds__(MODE == kModeGatherC4 ? kThreadsGather : kThreadsBase, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                    const ConvKernelParams p) {
+                    const __grid_constant__ CUtensorMap tmapOut, const ConvKernelParams p) {
   using C = Cfg<BLOCK_N>;
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B operand tiles need 1024-byte alignment
@@ -75,22 +94,21 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   const int lane = threadIdx.x & 31;
   const int num_tiles = p.m_tiles * p.n_tiles;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == 1 && lane == 0) {
     if (MODE != kModeGatherC4) tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
-  }
-  if (warp == 1 && lane == 0) {
+    if (!p.out_f32) tma_prefetch_desc(&tmapOut);
     for (int i = 0; i < C::kStages; ++i) {
-      mbar_init(smem_u32(&full_bar[i]), MODE == kModeGatherC4 ? 1 + 128 : 1);
+      mbar_init(smem_u32(&full_bar[i]), MODE == kModeGatherC4 ? 1 + kGatherWarps * 32 : 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), 128);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), kEpiWarps * 32);
     }
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<C::kTmemCols>(smem_u32(tmem_ptr_smem));
+  if (warp == 0) tmem_alloc<C::kTmemCols>(smem_u32(tmem_ptr_smem));
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -163,50 +181,88 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================== epilogue =====================
-    const int ew = warp - 4;  // == warp % 4: this warp may touch TMEM lanes [32*ew, 32*ew+32)
-    uint8_t* stg = staging + ew * 2048;
-    const uint32_t stg_u32 = smem_u32(stg);
+  } else if (warp < 2 + kEpiWarps) {
+    // ===================== epilogue: 8 warps =====================
+    // warp -> TMEM lane group (warp % 4, a hardware rule) and half of the tile's 32-column chunks.
+    // Per chunk: TMEM -> regs, scale/shift/act, (+ residual, prefetched one chunk ahead with
+    // coalesced loads and transposed through smem), act, bf16 pack -> SWIZZLE_64B staging ->
+    // one TMA store (clips the M / C_out tails in hardware).
+    constexpr int kChunks = BLOCK_N / 32;
+    constexpr int kChunksPerWarp = kChunks / 2;
+    const int lg = warp & 3;
+    const int half = (warp - 2) >> 2;
+    uint8_t* stg = staging + (warp - 2) * 4096;
     const int swz_own = (lane >> 1) & 3;
+    const int q4 = lane & 3, r8 = lane >> 2;
+    const bool has_res = p.residual != nullptr;
+    uint32_t nstore = 0;
     uint32_t acc = 0, acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const int m0 = m_tile * kBlockM + ew * 32, n0 = n_tile * BLOCK_N;
+      const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
+      const int c_first = half * kChunksPerWarp;
+      uint4 rpre[4];
+      auto load_res = [&](int cb) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int gr = m0 + r8 + 8 * i, col = cb + q4 * 8;
+          rpre[i] = make_uint4(0, 0, 0, 0);
+          if (gr < p.M && col < p.Cout)
+            rpre[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(gr) * p.Cout + col));
+        }
+      };
+      // chunks of this tile that hold real output channels and belong to this warp (C_out tail)
+      const int n_my = min(kChunksPerWarp, max(0, (p.Cout - (n0 + c_first * 32) + 31) / 32));
+      if (has_res && n_my > 0) load_res(n0 + c_first * 32);  // overlaps the wait below
       mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
       tcgen05_fence_after();
+      if (n_my == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // nothing to read: release at once
 #pragma unroll 1
-      for (int chunk = 0; chunk < BLOCK_N / 32; ++chunk) {
+      for (int ci = 0; ci < n_my; ++ci) {
+        const int chunk = c_first + ci;
         const int cbase = n0 + chunk * 32;
-        if (cbase >= p.Cout) break;
+        uint8_t* buf = stg + (nstore & 1) * 2048;
+        if (!p.out_f32) {
+          // the TMA store issued two chunks ago read this buffer: make sure it has finished reading
+          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          __syncwarp();
+        }
+        if (has_res) {
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int r = r8 + 8 * i;
+            *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4)) = rpre[i];
+          }
+          __syncwarp();
+          if (ci + 1 < n_my) load_res(cbase + 32);  // prefetch the next chunk
+        }
         uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+        float4 sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          sc[j] = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + j);
+          sh[j] = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + j);
+        }
         tmem_ld_wait();
+        if (ci == n_my - 1) {
+          // this warp's last read of the accumulator: hand the TMEM buffer back to the MMA warp early
+          tcgen05_fence_before();
+          mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
+        }
         float f[32];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + j);
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + j);
-          f[4 * j + 0] = apply_act(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x), p.act1, p.alpha1);
-          f[4 * j + 1] = apply_act(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), p.act1, p.alpha1);
-          f[4 * j + 2] = apply_act(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), p.act1, p.alpha1);
-          f[4 * j + 3] = apply_act(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), p.act1, p.alpha1);
+          f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc[j].x, sh[j].x);
+          f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc[j].y, sh[j].y);
+          f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc[j].z, sh[j].z);
+          f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc[j].w, sh[j].w);
         }
-        if (p.residual != nullptr) {
-          // coalesced read of the 32 x 32 residual block (64 B row segments), transposed through smem
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {  // 4 x (8 rows x 64 B) = this warp's 32 rows
-            const int r = (lane >> 2) + 8 * i, q4 = lane & 3;
-            const int gr = m0 + r, col = cbase + q4 * 8;
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (gr < p.M && col < p.Cout)
-              val = __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(gr) * p.Cout + col));
-            *reinterpret_cast<uint4*>(stg + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4)) = val;
-          }
-          __syncwarp();
+        act_inplace(f, p.act1, p.alpha1);
+        if (has_res) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint4 val = *reinterpret_cast<const uint4*>(stg + lane * 64 + ((j ^ swz_own) << 4));
+            const uint4 val = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((j ^ swz_own) << 4));
             const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&val);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -215,12 +271,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
               f[8 * j + 2 * e + 1] += rr.y;
             }
           }
-          __syncwarp();
+          __syncwarp();  // every lane has read its residual row before the buffer is overwritten
         }
-        if (p.act2 != TLXCV_ACT_NONE) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], p.act2, p.alpha2);
-        }
+        act_inplace(f, p.act2, p.alpha2);
         if (p.out_f32) {
           const int gr = m0 + lane;
           if (gr < p.M) {
@@ -238,35 +291,33 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
             o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
             o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            *reinterpret_cast<uint4*>(stg + lane * 64 + ((j ^ swz_own) << 4)) = o;
+            *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ swz_own) << 4)) = o;
           }
+          fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
           __syncwarp();
-          __nv_bfloat16* outp = reinterpret_cast<__nv_bfloat16*>(p.out);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = (lane >> 2) + 8 * i, q4 = lane & 3;
-            const int gr = m0 + r, col = cbase + q4 * 8;
-            const uint4 val = *reinterpret_cast<const uint4*>(stg + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4));
-            if (gr < p.M && col < p.Cout)
-              *reinterpret_cast<uint4*>(outp + static_cast<size_t>(gr) * p.Cout + col) = val;
+          if (lane == 0) {
+            tma_store_2d(&tmapOut, smem_u32(buf), cbase, m0);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
-          __syncwarp();
+          ++nstore;
         }
       }
-      (void)stg_u32;
-      tcgen05_fence_before();
-      mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
       if (++acc == 2) {
         acc = 0;
         acc_phase ^= 1;
       }
     }
-  } else if (MODE == kModeGatherC4 && warp >= 8) {
-    // ===================== gather producers (C_in <= 4 stems) =====================
+    if (!p.out_f32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  } else if (MODE == kModeGatherC4) {
+    // ===================== gather producers (C_in <= 4 stems): 8 warps =====================
     // K layout of one 64-wide block: r_per_kb filter rows x KR elements, element = s*4 + c.
-    const int t = threadIdx.x - 256;  // A-tile row owned by this thread
+    // Thread -> (A-tile row, 4 of the 8 16-byte chunks of that row): all 8 loads of a K block are
+    // issued before the 4 swizzled 16 B stores.
+    const int g = threadIdx.x - kThreadsBase;
+    const int t = g & 127;         // A-tile row
+    const int chalf = g >> 7;      // chunks [4*chalf, 4*chalf+4)
     const int r_per_kb = kBlockK / p.KR;
-    const int chunks_per_row = p.KR / 8;  // 16 B chunks (two taps) per filter row
+    const int cpr_shift = p.KR == 16 ? 1 : 2;  // log2(16-byte chunks per filter row)
     const int PQ = p.P * p.Q;
     PipeState ps;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -279,22 +330,27 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const int ih0 = op * p.stride - p.pad, iw0 = oq * p.stride - p.pad;
       const uint2* img_base = reinterpret_cast<const uint2*>(p.in_c4) + static_cast<size_t>(img) * p.H * p.W;
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
-        uint8_t* a_row = smem + ps.stage * C::kStageBytes + t * 128;
-        for (int slot = 0; slot < r_per_kb; ++slot) {
+        uint2 lo[4], hi[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = chalf * 4 + u;
+          const int slot = chunk >> cpr_shift, j = chunk & ((1 << cpr_shift) - 1);
           const int r = kb * r_per_kb + slot;
           const int ih = ih0 + r * p.dil;
           const bool rok = row_ok && r < p.R && ih >= 0 && ih < p.H;
           const uint2* rowp = img_base + static_cast<size_t>(rok ? ih : 0) * p.W;
-          for (int j = 0; j < chunks_per_row; ++j) {
-            uint2 lo = make_uint2(0, 0), hi = make_uint2(0, 0);
-            const int s0 = 2 * j, s1 = 2 * j + 1;
-            const int w0 = iw0 + s0 * p.dil, w1 = iw0 + s1 * p.dil;
-            if (rok && s0 < p.S && w0 >= 0 && w0 < p.W) lo = __ldg(rowp + w0);
-            if (rok && s1 < p.S && w1 >= 0 && w1 < p.W) hi = __ldg(rowp + w1);
-            const int chunk = slot * chunks_per_row + j;
-            *reinterpret_cast<uint4*>(a_row + ((chunk ^ (t & 7)) << 4)) = make_uint4(lo.x, lo.y, hi.x, hi.y);
-          }
+          const int s0 = 2 * j, s1 = 2 * j + 1;
+          const int w0 = iw0 + s0 * p.dil, w1 = iw0 + s1 * p.dil;
+          lo[u] = make_uint2(0, 0), hi[u] = make_uint2(0, 0);
+          if (rok && s0 < p.S && w0 >= 0 && w0 < p.W) lo[u] = __ldg(rowp + w0);
+          if (rok && s1 < p.S && w1 >= 0 && w1 < p.W) hi[u] = __ldg(rowp + w1);
+        }
+        mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+        uint8_t* a_row = smem + ps.stage * C::kStageBytes + t * 128;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int chunk = chalf * 4 + u;
+          *reinterpret_cast<uint4*>(a_row + ((chunk ^ (t & 7)) << 4)) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
         }
         fence_proxy_async_smem();  // make the generic-proxy stores visible to tcgen05.mma's smem reads
         mbar_arrive(smem_u32(&full_bar[ps.stage]));
@@ -305,7 +361,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) {
+  if (warp == 0) {
     tcgen05_fence_after();
     tmem_dealloc<C::kTmemCols>(tmem_base);
   }
@@ -340,13 +396,13 @@ std::string load_driver_entry_points() {
 }
 
 std::string encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer, uint64_t row_bytes,
-                      uint32_t box_inner, uint32_t box_outer) {
+                      uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   cuuint64_t dims[2] = {inner, outer};
   cuuint64_t strides[1] = {row_bytes};
   cuuint32_t box[2] = {box_inner, box_outer};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = g_encode_tiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -385,7 +441,7 @@ std::string encode_im2col(CUtensorMap* map, const void* base, int N, int H, int 
 
 template <int BLOCK_N, int MODE>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
-  conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.p);
+  conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.p);
   return cudaGetLastError();
 }
 
@@ -430,7 +486,7 @@ cudaError_t tc_conv_set_attributes() {
 
 std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
                             int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
-                            int pad, int dil, int groups, int force_block_n) {
+                            int pad, int dil, int groups, int force_block_n, void* out_bf16) {
   std::string err = load_driver_entry_points();
   if (!err.empty()) return err;
   memset(&L, 0, sizeof L);
@@ -491,7 +547,7 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   p.n_tiles = (Cout + block_n - 1) / block_n;
   L.mode = mode;
   L.block_n = block_n;
-  L.threads = mode == kModeGatherC4 ? 384 : 256;
+  L.threads = mode == kModeGatherC4 ? kThreadsGather : kThreadsBase;
   L.smem = smem_for(block_n);
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   L.grid = static_cast<int>(std::min<long long>(tiles, sm_count));
@@ -508,6 +564,13 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   } else {
     L.tmapA = L.tmapB;  // unused
   }
+  if (!err.empty()) return err;
+  // output [M][Cout] bf16 written by per-warp TMA stores of 32 rows x 32 channels (64 B rows, SWIZZLE_64B);
+  // fp32 outputs (logits) are written with direct stores and leave the map unused
+  if (out_bf16)
+    err = encode_2d(&L.tmapOut, out_bf16, Cout, p.M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+  else
+    L.tmapOut = L.tmapB;
   return err;
 }
 

@@ -58,9 +58,9 @@ struct tlxcv_plan {
   uint8_t* arena = nullptr;
   size_t arena_bytes = 0;
   std::vector<void*> owned;
-  // CUDA graph cache (one entry: same external pointers => replay)
-  cudaGraphExec_t graph_exec = nullptr;
-  std::vector<const void*> graph_key;
+  // CUDA graph cache keyed by the external pointers (same pointers => replay); a few entries so that
+  // double-buffered callers do not re-capture every step
+  std::vector<std::pair<std::vector<const void*>, cudaGraphExec_t>> graphs;
   // host-run staging
   std::vector<void*> stage_in, stage_out;
 };
@@ -245,8 +245,13 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   const __nv_bfloat16* act_in = reinterpret_cast<const __nv_bfloat16*>(p->arena + in.offset);
   int force_bn = 0;
   if (const char* e = getenv("TLXCV_FORCE_BLOCK_N")) force_bn = atoi(e);
+  void* out_bf16 = nullptr;
+  if (out.d.dtype != TLXCV_F32) {
+    if (out.d.role != TLXCV_ROLE_INTERNAL) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: bf16 output must be an internal tensor");
+    out_bf16 = p->arena + out.offset;
+  }
   std::string err = tc_conv_prepare(op.tc, ctx->sm_count, act_in, N, H, W, C, in.cs, w, Ktot, K, R, S, stride, pad, dil,
-                                    groups, force_bn);
+                                    groups, force_bn, out_bf16);
   if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
   ConvKernelParams& kp = op.tc.p;
   kp.scale = op.scale, kp.shift = op.shift;
@@ -526,7 +531,7 @@ int tlxcv_plan_destroy(tlxcv_plan* p) {
   if (!p) return TLXCV_OK;
   cudaSetDevice(p->ctx->device);
   cudaDeviceSynchronize();
-  if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+  for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
   for (void* q : p->owned) cudaFree(q);
   for (void* q : p->stage_in) cudaFree(q);
   for (void* q : p->stage_out) cudaFree(q);
@@ -543,10 +548,13 @@ int tlxcv_plan_run(tlxcv_plan* p, const void* const* inputs, void* const* output
   std::vector<const void*> key;
   for (size_t i = 0; i < p->input_ids.size(); ++i) key.push_back(inputs[i]);
   for (size_t i = 0; i < p->output_ids.size(); ++i) key.push_back(outputs[i]);
-  if (!p->graph_exec || key != p->graph_key) {
-    if (p->graph_exec) {
-      cudaGraphExecDestroy(p->graph_exec);
-      p->graph_exec = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  for (auto& g : p->graphs)
+    if (g.first == key) exec = g.second;
+  if (!exec) {
+    if (p->graphs.size() >= 8) {  // bounded cache: drop the oldest capture
+      cudaGraphExecDestroy(p->graphs.front().second);
+      p->graphs.erase(p->graphs.begin());
     }
     cudaStream_t cap;
     TLX_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
@@ -563,15 +571,12 @@ int tlxcv_plan_run(tlxcv_plan* p, const void* const* inputs, void* const* output
       return rc;
     }
     if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&p->graph_exec, graph, 0);
+    e = cudaGraphInstantiate(&exec, graph, 0);
     cudaGraphDestroy(graph);
-    if (e != cudaSuccess) {
-      p->graph_exec = nullptr;
-      return fail(ctx, TLXCV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
-    }
-    p->graph_key = key;
+    if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    p->graphs.emplace_back(key, exec);
   }
-  TLX_CUDA(ctx, cudaGraphLaunch(p->graph_exec, st));
+  TLX_CUDA(ctx, cudaGraphLaunch(exec, st));
   return TLXCV_OK;
 }
 
