@@ -35,7 +35,9 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
 constexpr int kEpiWarps = 8;                    // warps 2..9
 constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
 constexpr int kStagingBytes = kEpiWarps * 4096; // per epilogue warp: 2 x (32 rows x 64 B), SWIZZLE_64B
+constexpr int kScaleCacheBytes = 2 * 256 * 4;   // [scale | shift] of one N tile (used when the layer has one N tile)
 constexpr int kBarrierBytes = 256;
+constexpr int kResDepth = 3;                    // residual prefetch distance, in 32x32 chunks
 constexpr int kMaxStages = 8;
 constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
 constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 576
@@ -46,7 +48,7 @@ struct Cfg {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: a power of two >= 32
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kBarrierBytes + 1024;
+  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kScaleCacheBytes + kBarrierBytes;
 };
 
 struct PipeState {
@@ -79,11 +81,13 @@ __global__ void __launch_bounds__(MODE == kModeGatherC4 ? kThreadsGather : kThre
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapOut, const ConvKernelParams p) {
   using C = Cfg<BLOCK_N>;
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B operand tiles need 1024-byte alignment
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // SWIZZLE_128B operand tiles need 1024-byte alignment; no pointer casts through integers here, so
+  // that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0) __trap();
   uint8_t* staging = smem + C::kStages * C::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes);
+  float* sc_cache = reinterpret_cast<float*>(staging + kStagingBytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes + kScaleCacheBytes);
   uint64_t* full_bar = bars;                       // [kStages]  operands landed
   uint64_t* empty_bar = bars + kMaxStages;         // [kStages]  MMAs that read the stage retired
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]        accumulator complete
@@ -109,6 +113,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<C::kTmemCols>(smem_u32(tmem_ptr_smem));
+  const bool sc_cached = p.n_tiles == 1;  // one N tile: scale/shift never change, keep them in smem
+  if (sc_cached && warp >= 2 && warp < 2 + kEpiWarps) {
+    for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiWarps * 32) {
+      sc_cache[i] = p.scale[i];
+      sc_cache[256 + i] = p.shift[i];
+    }
+  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -131,21 +142,24 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           base_w = oq * p.stride - p.pad;
         }
         const int c_base = p.a_chan_from_n ? n_tile * BLOCK_N : 0;
+        // no divisions in the K loop: this single thread's per-iteration latency bounds small-N tiles
+        int r = 0, sx = 0, cb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
           const uint32_t a_dst = smem_u32(smem + ps.stage * C::kStageBytes);
-          const uint32_t b_dst = a_dst + kABytes;
           mbar_arrive_expect_tx(bar, MODE == kModeGatherC4 ? C::kBBytes : C::kStageBytes);
           if (MODE == kModeTiled) {
             tma_load_2d(a_dst, &tmapA, bar, kb * kBlockK, m0);
           } else if (MODE == kModeIm2col) {
-            const int tap = kb / p.kb_per_tap, cb = kb - tap * p.kb_per_tap;
-            const int r = tap / p.S, s = tap - r * p.S;
             tma_load_im2col_4d(a_dst, &tmapA, bar, c_base + cb * kBlockK, base_w, base_h, img,
-                               static_cast<uint16_t>(s * p.dil), static_cast<uint16_t>(r * p.dil));
+                               static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+            if (++cb == p.kb_per_tap) {
+              cb = 0;
+              if (++sx == p.S) sx = 0, ++r;
+            }
           }
-          tma_load_2d(b_dst, &tmapB, bar, kb * kBlockK, n0);
+          tma_load_2d(a_dst + kABytes, &tmapB, bar, kb * kBlockK, n0);
           ps.advance(C::kStages);
         }
       }
@@ -184,46 +198,74 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   } else if (warp < 2 + kEpiWarps) {
     // ===================== epilogue: 8 warps =====================
     // warp -> TMEM lane group (warp % 4, a hardware rule) and half of the tile's 32-column chunks.
-    // Per chunk: TMEM -> regs, scale/shift/act, (+ residual, prefetched one chunk ahead with
-    // coalesced loads and transposed through smem), act, bf16 pack -> SWIZZLE_64B staging ->
-    // one TMA store (clips the M / C_out tails in hardware).
+    // The warp's work is a flat sequence of (tile, chunk) items.  Per item: TMEM -> regs,
+    // scale/shift/act, + residual (coalesced loads issued kResDepth items ahead, transposed through
+    // smem), act, bf16 pack -> SWIZZLE_64B staging -> one TMA store (clips the M / C_out tails).
     constexpr int kChunks = BLOCK_N / 32;
-    constexpr int kChunksPerWarp = kChunks / 2;
+    constexpr int kCpw = kChunks / 2;  // chunks per warp per tile: 1, 2 or 4
+    constexpr bool kRes = MODE != kModeGatherC4;  // stems never carry a residual (keeps their register count low)
     const int lg = warp & 3;
     const int half = (warp - 2) >> 2;
+    const int c_first = half * kCpw;
     uint8_t* stg = staging + (warp - 2) * 4096;
     const int swz_own = (lane >> 1) & 3;
     const int q4 = lane & 3, r8 = lane >> 2;
-    const bool has_res = p.residual != nullptr;
+    const bool has_res = kRes && p.residual != nullptr;
+
+    struct Cursor {  // walks this warp's items in order
+      int tile, ci, m0, n0, n_my;
+    };
+    auto place = [&](Cursor& c) {
+      const int m_tile = c.tile / p.n_tiles, n_tile = c.tile - m_tile * p.n_tiles;
+      c.m0 = m_tile * kBlockM + lg * 32;
+      c.n0 = n_tile * BLOCK_N;
+      c.n_my = min(kCpw, max(0, (p.Cout - (c.n0 + c_first * 32) + 31) / 32));  // chunks holding real channels
+    };
+    auto advance = [&](Cursor& c) {
+      if (++c.ci == kCpw) {
+        c.ci = 0;
+        c.tile += gridDim.x;
+        if (c.tile < num_tiles) place(c);
+      }
+    };
+    auto load_res = [&](const Cursor& c, uint4 (&rp)[4]) {
+      if (c.tile >= num_tiles || c.ci >= c.n_my) return;
+      const int cb = c.n0 + (c_first + c.ci) * 32;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int gr = c.m0 + r8 + 8 * i, col = cb + q4 * 8;
+        rp[i] = make_uint4(0, 0, 0, 0);
+        if (gr < p.M && col < p.Cout)
+          rp[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(gr) * p.Cout + col));
+      }
+    };
+
+    Cursor cur{static_cast<int>(blockIdx.x), 0, 0, 0, 0}, pre{static_cast<int>(blockIdx.x), 0, 0, 0, 0};
+    if (cur.tile < num_tiles) place(cur), place(pre);
+    uint4 rp0[4], rp1[4], rp2[4];
+    if (has_res) {
+      load_res(pre, rp0), advance(pre);
+      load_res(pre, rp1), advance(pre);
+      load_res(pre, rp2), advance(pre);
+    }
     uint32_t nstore = 0;
     uint32_t acc = 0, acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
-      const int c_first = half * kChunksPerWarp;
-      uint4 rpre[4];
-      auto load_res = [&](int cb) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int gr = m0 + r8 + 8 * i, col = cb + q4 * 8;
-          rpre[i] = make_uint4(0, 0, 0, 0);
-          if (gr < p.M && col < p.Cout)
-            rpre[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(gr) * p.Cout + col));
-        }
-      };
-      // chunks of this tile that hold real output channels and belong to this warp (C_out tail)
-      const int n_my = min(kChunksPerWarp, max(0, (p.Cout - (n0 + c_first * 32) + 31) / 32));
-      if (has_res && n_my > 0) load_res(n0 + c_first * 32);  // overlaps the wait below
-      mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
-      tcgen05_fence_after();
-      if (n_my == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // nothing to read: release at once
-#pragma unroll 1
-      for (int ci = 0; ci < n_my; ++ci) {
-        const int chunk = c_first + ci;
-        const int cbase = n0 + chunk * 32;
+
+    auto step = [&](uint4 (&rp)[4]) {
+      if (cur.tile >= num_tiles) return;
+      if (cur.ci == 0) {
+        mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
+        tcgen05_fence_after();
+        if (cur.n_my == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // nothing to read: release at once
+      }
+      if (cur.ci < cur.n_my) {
+        const int chunk = c_first + cur.ci;
+        const int cbase = cur.n0 + chunk * 32;
         uint8_t* buf = stg + (nstore & 1) * 2048;
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
         if (!p.out_f32) {
-          // the TMA store issued two chunks ago read this buffer: make sure it has finished reading
+          // the TMA store issued two items ago read this buffer: make sure it has finished reading
           if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           __syncwarp();
         }
@@ -231,32 +273,38 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const int r = r8 + 8 * i;
-            *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4)) = rpre[i];
+            *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4)) = rp[i];
           }
           __syncwarp();
-          if (ci + 1 < n_my) load_res(cbase + 32);  // prefetch the next chunk
-        }
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
-        float4 sc[8], sh[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          sc[j] = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + j);
-          sh[j] = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + j);
         }
         tmem_ld_wait();
-        if (ci == n_my - 1) {
+        if (cur.ci == cur.n_my - 1) {
           // this warp's last read of the accumulator: hand the TMEM buffer back to the MMA warp early
           tcgen05_fence_before();
           mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
         }
         float f[32];
+        if (sc_cached) {
+          const float4* scp = reinterpret_cast<const float4*>(sc_cache + chunk * 32);
+          const float4* shp = reinterpret_cast<const float4*>(sc_cache + 256 + chunk * 32);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc[j].x, sh[j].x);
-          f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc[j].y, sh[j].y);
-          f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc[j].z, sh[j].z);
-          f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc[j].w, sh[j].w);
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = scp[j], sh = shp[j];
+            f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+            f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+            f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + j);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + j);
+            f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
+            f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
+            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
+            f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
+          }
         }
         act_inplace(f, p.act1, p.alpha1);
         if (has_res) {
@@ -275,7 +323,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
         act_inplace(f, p.act2, p.alpha2);
         if (p.out_f32) {
-          const int gr = m0 + lane;
+          const int gr = cur.m0 + lane;
           if (gr < p.M) {
             float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(gr) * p.Cout + cbase;
 #pragma unroll
@@ -296,16 +344,26 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmapOut, smem_u32(buf), cbase, m0);
+            tma_store_2d(&tmapOut, smem_u32(buf), cbase, cur.m0);
             asm volatile("cp.async.bulk.commit_group;" ::: "memory");
           }
           ++nstore;
         }
       }
-      if (++acc == 2) {
-        acc = 0;
-        acc_phase ^= 1;
+      if (cur.ci == kCpw - 1) {
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
       }
+      advance(cur);
+      if (has_res) load_res(pre, rp), advance(pre);  // refill this slot for the item kResDepth ahead
+    };
+    static_assert(kResDepth == 3, "the register ring below is unrolled for depth 3");
+    while (cur.tile < num_tiles) {
+      step(rp0);
+      step(rp1);
+      step(rp2);
     }
     if (!p.out_f32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   } else if (MODE == kModeGatherC4) {
