@@ -34,10 +34,10 @@ constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
 constexpr int kEpiWarps = 8;                    // warps 2..9
 constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
-constexpr int kStagingBytes = kEpiWarps * 4096; // per epilogue warp: 2 x (32 rows x 64 B), SWIZZLE_64B
+constexpr int kRing = 4;                        // per epilogue warp: ring of 4 x (32 rows x 64 B) SWIZZLE_64B buffers
+constexpr int kStagingBytes = kEpiWarps * kRing * 2048;
 constexpr int kScaleCacheBytes = 2 * 256 * 4;   // [scale | shift] of one N tile (used when the layer has one N tile)
-constexpr int kBarrierBytes = 256;
-constexpr int kResDepth = 3;                    // residual prefetch distance, in 32x32 chunks
+constexpr int kBarrierBytes = 512;              // pipeline barriers + kEpiWarps * kRing residual barriers
 constexpr int kMaxStages = 8;
 constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
 constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 576
@@ -46,7 +46,7 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N == 256 ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 6);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: a power of two >= 32
   static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kScaleCacheBytes + kBarrierBytes;
 };
@@ -76,10 +76,181 @@ __device__ __forceinline__ void act_inplace(float (&f)[N], int act, float alpha)
   }
 }
 
+// Everything one epilogue warp needs, hoisted out of the loops (kernel parameters live in constant
+// memory; re-reading them through the uniform datapath inside the item loop costs latency).
+struct EpiArgs {
+  uint32_t tmem_base, tmem_full_bar, tmem_empty_bar, ring, res_bar;  // smem addresses are shared-space offsets
+  const float* sc_cache;  // smem [scale(256) | shift(256)] when the layer has a single N tile, else nullptr
+  const float* scale;
+  const float* shift;
+  float* out_f32;
+  const CUtensorMap* tmap_out;
+  const CUtensorMap* tmap_res;
+  int M, Cout, n_tiles, num_tiles, first_tile, tile_stride;
+  float alpha1, alpha2;
+};
+
+template <int ACT>
+__device__ __forceinline__ float act1f(float v, float alpha) {
+  if (ACT == TLXCV_ACT_RELU) return fmaxf(v, 0.0f);
+  if (ACT == TLXCV_ACT_RELU6) return fminf(fmaxf(v, 0.0f), 6.0f);
+  if (ACT == TLXCV_ACT_LEAKY) return v > 0.0f ? v : v * alpha;
+  return v;
+}
+
+// One epilogue warp: TMEM lane group `lg` (rows), column group `cgroup`.  The warp's work is the
+// sequence of its valid 32x32 chunks ("items") over the CTA's tiles.  Per item:
+//   tcgen05.ld -> fp32 scale/shift -> act1 -> (+ residual) -> act2 -> bf16 -> TMA store.
+// The residual chunk is fetched by TMA into a kRing-deep ring of 2 KB SWIZZLE_64B buffers three
+// items ahead; each lane reads ITS row of the buffer, computes, and writes its output row back into
+// the same buffer, which one TMA store then drains.  No per-element global addressing, no
+// predicates: TMA clips the M and C_out tails.
+template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32>
+__device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
+  constexpr int kCpw = (BLOCK_N / 32) / 2;  // chunks per warp per tile
+  const int c_first = cgroup * kCpw;
+  const int swz_own = (lane >> 1) & 3;
+  const uint32_t own_row = a.ring + lane * 64;
+
+  // prefetch cursor (only lane 0 advances it): walks the same item sequence, kRing-1 items ahead
+  int pf_tile = a.first_tile, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0;
+  uint32_t pf = 0;
+  auto pf_place = [&]() {
+    const int m_tile = pf_tile / a.n_tiles, n_tile = pf_tile - m_tile * a.n_tiles;
+    pf_m0 = m_tile * kBlockM + lg * 32;
+    pf_n0 = n_tile * BLOCK_N;
+    pf_nmy = min(kCpw, max(0, (a.Cout - (pf_n0 + c_first * 32) + 31) / 32));
+  };
+  auto pf_issue = [&]() {  // issue the residual load of the next valid item, if any
+    while (pf_tile < a.num_tiles && pf_ci >= pf_nmy) {
+      pf_ci = 0;
+      pf_tile += a.tile_stride;
+      if (pf_tile < a.num_tiles) pf_place();
+    }
+    if (pf_tile >= a.num_tiles) return;
+    const uint32_t slot = pf & (kRing - 1);
+    const uint32_t bar = a.res_bar + slot * 8;
+    mbar_arrive_expect_tx(bar, 2048);
+    tma_load_2d(a.ring + slot * 2048, a.tmap_res, bar, pf_n0 + (c_first + pf_ci) * 32, pf_m0);
+    ++pf;
+    ++pf_ci;
+  };
+  if (RES && lane == 0) {
+    if (pf_tile < a.num_tiles) pf_place();
+#pragma unroll
+    for (int k = 0; k < kRing - 1; ++k) pf_issue();
+  }
+
+  uint32_t it = 0;  // items processed
+  uint32_t acc = 0, acc_phase = 0;
+  for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
+    const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+    const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
+    const int n_my = min(kCpw, max(0, (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
+    mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
+    tcgen05_fence_after();
+    if (n_my == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);  // nothing to read: release at once
+#pragma unroll 1
+    for (int ci = 0; ci < n_my; ++ci, ++it) {
+      const int chunk = c_first + ci;
+      const int cbase = n0 + chunk * 32;
+      const uint32_t slot = it & (kRing - 1);
+      uint32_t v[32];
+      tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+      if (RES) {
+        mbar_wait(a.res_bar + slot * 8, (it / kRing) & 1);  // residual chunk has landed in the ring slot
+      } else if (!F32) {
+        // the TMA store that used this slot kRing items ago must have finished reading it
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        __syncwarp();
+      }
+      tmem_ld_wait();
+      if (ci == n_my - 1) {
+        // this warp's last read of the accumulator: hand the TMEM buffer back to the MMA warp early
+        tcgen05_fence_before();
+        mbar_arrive(a.tmem_empty_bar + acc * 8);
+      }
+      float f[32];
+      if (a.sc_cache != nullptr) {
+        const float4* scp = reinterpret_cast<const float4*>(a.sc_cache + chunk * 32);
+        const float4* shp = reinterpret_cast<const float4*>(a.sc_cache + 256 + chunk * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = scp[j], sh = shp[j];
+          f[4 * j + 0] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x), a.alpha1);
+          f[4 * j + 1] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), a.alpha1);
+          f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), a.alpha1);
+          f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), a.alpha1);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + cbase) + j);
+          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + cbase) + j);
+          f[4 * j + 0] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x), a.alpha1);
+          f[4 * j + 1] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), a.alpha1);
+          f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), a.alpha1);
+          f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), a.alpha1);
+        }
+      }
+      if (F32) {
+        const int gr = m0 + lane;
+        if (gr < a.M) {
+          float* dst = a.out_f32 + static_cast<size_t>(gr) * a.Cout + cbase;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (cbase + 4 * j < a.Cout)
+              reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        }
+        continue;
+      }
+      const uint32_t row = own_row + slot * 2048;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint32_t addr = row + ((j ^ swz_own) << 4);
+        if (RES) {
+          uint4 val;
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(addr));
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&val);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 rr = __bfloat1622float2(h[e]);
+            f[8 * j + 2 * e] = act1f<ACT2>(f[8 * j + 2 * e] + rr.x, a.alpha2);
+            f[8 * j + 2 * e + 1] = act1f<ACT2>(f[8 * j + 2 * e + 1] + rr.y, a.alpha2);
+          }
+        }
+        const uint32_t o0 = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), o1 = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
+        const uint32_t o2 = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), o3 = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
+        // each lane only ever touches ITS row of the slot, so no warp sync is needed between the
+        // residual read and this write
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+      }
+      fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
+      __syncwarp();
+      if (lane == 0) {
+        tma_store_2d(a.tmap_out, a.ring + slot * 2048, cbase, m0);
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (RES) {
+          // refill the slot of item it+3 (== the slot item it-1 used): every store but the one just
+          // committed must have finished reading its buffer
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          pf_issue();
+        }
+      }
+    }
+    if (++acc == 2) {
+      acc = 0;
+      acc_phase ^= 1;
+    }
+  }
+  if (!F32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <int BLOCK_N, int MODE>
 __global__ void __launch_bounds__(MODE == kModeGatherC4 ? kThreadsGather : kThreadsBase, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
-                    const __grid_constant__ CUtensorMap tmapOut, const ConvKernelParams p) {
+                    const __grid_constant__ CUtensorMap tmapOut, const __grid_constant__ CUtensorMap tmapRes,
+                    const ConvKernelParams p) {
   using C = Cfg<BLOCK_N>;
   // SWIZZLE_128B operand tiles need 1024-byte alignment; no pointer casts through integers here, so
   // that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
@@ -93,6 +264,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]        accumulator complete
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]        accumulator drained by the epilogue
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = bars + 2 * kMaxStages + 8;   // [kEpiWarps][kRing] residual chunk landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -110,6 +282,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
       mbar_init(smem_u32(&tmem_empty_bar[i]), kEpiWarps * 32);
     }
+    for (int i = 0; i < kEpiWarps * kRing; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    if (!p.out_f32 && p.residual != nullptr) tma_prefetch_desc(&tmapRes);
     fence_barrier_init();
   }
   if (warp == 0) tmem_alloc<C::kTmemCols>(smem_u32(tmem_ptr_smem));
@@ -196,176 +370,35 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       }
     }
   } else if (warp < 2 + kEpiWarps) {
-    // ===================== epilogue: 8 warps =====================
-    // warp -> TMEM lane group (warp % 4, a hardware rule) and half of the tile's 32-column chunks.
-    // The warp's work is a flat sequence of (tile, chunk) items.  Per item: TMEM -> regs,
-    // scale/shift/act, + residual (coalesced loads issued kResDepth items ahead, transposed through
-    // smem), act, bf16 pack -> SWIZZLE_64B staging -> one TMA store (clips the M / C_out tails).
-    constexpr int kChunks = BLOCK_N / 32;
-    constexpr int kCpw = kChunks / 2;  // chunks per warp per tile: 1, 2 or 4
-    constexpr bool kRes = MODE != kModeGatherC4;  // stems never carry a residual (keeps their register count low)
-    const int lg = warp & 3;
-    const int half = (warp - 2) >> 2;
-    const int c_first = half * kCpw;
-    uint8_t* stg = staging + (warp - 2) * 4096;
-    const int swz_own = (lane >> 1) & 3;
-    const int q4 = lane & 3, r8 = lane >> 2;
-    const bool has_res = kRes && p.residual != nullptr;
-
-    struct Cursor {  // walks this warp's items in order
-      int tile, ci, m0, n0, n_my;
-    };
-    auto place = [&](Cursor& c) {
-      const int m_tile = c.tile / p.n_tiles, n_tile = c.tile - m_tile * p.n_tiles;
-      c.m0 = m_tile * kBlockM + lg * 32;
-      c.n0 = n_tile * BLOCK_N;
-      c.n_my = min(kCpw, max(0, (p.Cout - (c.n0 + c_first * 32) + 31) / 32));  // chunks holding real channels
-    };
-    auto advance = [&](Cursor& c) {
-      if (++c.ci == kCpw) {
-        c.ci = 0;
-        c.tile += gridDim.x;
-        if (c.tile < num_tiles) place(c);
-      }
-    };
-    auto load_res = [&](const Cursor& c, uint4 (&rp)[4]) {
-      if (c.tile >= num_tiles || c.ci >= c.n_my) return;
-      const int cb = c.n0 + (c_first + c.ci) * 32;
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int gr = c.m0 + r8 + 8 * i, col = cb + q4 * 8;
-        rp[i] = make_uint4(0, 0, 0, 0);
-        if (gr < p.M && col < p.Cout)
-          rp[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(gr) * p.Cout + col));
-      }
-    };
-
-    Cursor cur{static_cast<int>(blockIdx.x), 0, 0, 0, 0}, pre{static_cast<int>(blockIdx.x), 0, 0, 0, 0};
-    if (cur.tile < num_tiles) place(cur), place(pre);
-    uint4 rp0[4], rp1[4], rp2[4];
-    if (has_res) {
-      load_res(pre, rp0), advance(pre);
-      load_res(pre, rp1), advance(pre);
-      load_res(pre, rp2), advance(pre);
+    // ===================== epilogue: 8 warps (see epilogue_loop) =====================
+    constexpr bool kRes = MODE != kModeGatherC4;  // stems never carry a residual
+    EpiArgs a;
+    a.tmem_base = tmem_base;
+    a.tmem_full_bar = smem_u32(tmem_full_bar);
+    a.tmem_empty_bar = smem_u32(tmem_empty_bar);
+    a.ring = smem_u32(staging + (warp - 2) * (kRing * 2048));
+    a.res_bar = smem_u32(res_bar + (warp - 2) * kRing);
+    a.sc_cache = sc_cached ? sc_cache : nullptr;
+    a.scale = p.scale, a.shift = p.shift;
+    a.out_f32 = reinterpret_cast<float*>(p.out);
+    a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
+    a.M = p.M, a.Cout = p.Cout, a.n_tiles = p.n_tiles, a.num_tiles = num_tiles;
+    a.first_tile = blockIdx.x, a.tile_stride = gridDim.x;
+    a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
+    const int lg = warp & 3, cgroup = (warp - 2) >> 2;
+    const bool res = kRes && p.residual != nullptr;
+#define TLXCV_EPI(A1)                                                                                       \
+  if (p.out_f32) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, true>(a, lg, cgroup, lane);              \
+  else if (!res) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false>(a, lg, cgroup, lane);             \
+  else if (p.act2 == TLXCV_ACT_RELU) epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_RELU, false>(a, lg, cgroup, lane); \
+  else epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_NONE, false>(a, lg, cgroup, lane);
+    switch (p.act1) {
+      case TLXCV_ACT_RELU: TLXCV_EPI(TLXCV_ACT_RELU) break;
+      case TLXCV_ACT_RELU6: TLXCV_EPI(TLXCV_ACT_RELU6) break;
+      case TLXCV_ACT_LEAKY: TLXCV_EPI(TLXCV_ACT_LEAKY) break;
+      default: TLXCV_EPI(TLXCV_ACT_NONE) break;
     }
-    uint32_t nstore = 0;
-    uint32_t acc = 0, acc_phase = 0;
-
-    auto step = [&](uint4 (&rp)[4]) {
-      if (cur.tile >= num_tiles) return;
-      if (cur.ci == 0) {
-        mbar_wait(smem_u32(&tmem_full_bar[acc]), acc_phase);
-        tcgen05_fence_after();
-        if (cur.n_my == 0) mbar_arrive(smem_u32(&tmem_empty_bar[acc]));  // nothing to read: release at once
-      }
-      if (cur.ci < cur.n_my) {
-        const int chunk = c_first + cur.ci;
-        const int cbase = cur.n0 + chunk * 32;
-        uint8_t* buf = stg + (nstore & 1) * 2048;
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
-        if (!p.out_f32) {
-          // the TMA store issued two items ago read this buffer: make sure it has finished reading
-          if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
-          __syncwarp();
-        }
-        if (has_res) {
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int r = r8 + 8 * i;
-            *reinterpret_cast<uint4*>(buf + r * 64 + ((q4 ^ ((r >> 1) & 3)) << 4)) = rp[i];
-          }
-          __syncwarp();
-        }
-        tmem_ld_wait();
-        if (cur.ci == cur.n_my - 1) {
-          // this warp's last read of the accumulator: hand the TMEM buffer back to the MMA warp early
-          tcgen05_fence_before();
-          mbar_arrive(smem_u32(&tmem_empty_bar[acc]));
-        }
-        float f[32];
-        if (sc_cached) {
-          const float4* scp = reinterpret_cast<const float4*>(sc_cache + chunk * 32);
-          const float4* shp = reinterpret_cast<const float4*>(sc_cache + 256 + chunk * 32);
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 sc = scp[j], sh = shp[j];
-            f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-            f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-            f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const float4 sc = __ldg(reinterpret_cast<const float4*>(p.scale + cbase) + j);
-            const float4 sh = __ldg(reinterpret_cast<const float4*>(p.shift + cbase) + j);
-            f[4 * j + 0] = fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x);
-            f[4 * j + 1] = fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y);
-            f[4 * j + 2] = fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z);
-            f[4 * j + 3] = fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w);
-          }
-        }
-        act_inplace(f, p.act1, p.alpha1);
-        if (has_res) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const uint4 val = *reinterpret_cast<const uint4*>(buf + lane * 64 + ((j ^ swz_own) << 4));
-            const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&val);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 rr = __bfloat1622float2(h[e]);
-              f[8 * j + 2 * e] += rr.x;
-              f[8 * j + 2 * e + 1] += rr.y;
-            }
-          }
-          __syncwarp();  // every lane has read its residual row before the buffer is overwritten
-        }
-        act_inplace(f, p.act2, p.alpha2);
-        if (p.out_f32) {
-          const int gr = cur.m0 + lane;
-          if (gr < p.M) {
-            float* dst = reinterpret_cast<float*>(p.out) + static_cast<size_t>(gr) * p.Cout + cbase;
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              if (cbase + 4 * j < p.Cout)
-                reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint4 o;
-            o.x = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]);
-            o.y = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-            o.z = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]);
-            o.w = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
-            *reinterpret_cast<uint4*>(buf + lane * 64 + ((j ^ swz_own) << 4)) = o;
-          }
-          fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
-          __syncwarp();
-          if (lane == 0) {
-            tma_store_2d(&tmapOut, smem_u32(buf), cbase, cur.m0);
-            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-          }
-          ++nstore;
-        }
-      }
-      if (cur.ci == kCpw - 1) {
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
-        }
-      }
-      advance(cur);
-      if (has_res) load_res(pre, rp), advance(pre);  // refill this slot for the item kResDepth ahead
-    };
-    static_assert(kResDepth == 3, "the register ring below is unrolled for depth 3");
-    while (cur.tile < num_tiles) {
-      step(rp0);
-      step(rp1);
-      step(rp2);
-    }
-    if (!p.out_f32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#undef TLXCV_EPI
   } else if (MODE == kModeGatherC4) {
     // ===================== gather producers (C_in <= 4 stems): 8 warps =====================
     // K layout of one 64-wide block: r_per_kb filter rows x KR elements, element = s*4 + c.
@@ -499,7 +532,7 @@ std::string encode_im2col(CUtensorMap* map, const void* base, int N, int H, int 
 
 template <int BLOCK_N, int MODE>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
-  conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.p);
+  conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.p);
   return cudaGetLastError();
 }
 
@@ -544,7 +577,7 @@ cudaError_t tc_conv_set_attributes() {
 
 std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
                             int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
-                            int pad, int dil, int groups, int force_block_n, void* out_bf16) {
+                            int pad, int dil, int groups, int force_block_n, void* out_bf16, const void* residual_bf16) {
   std::string err = load_driver_entry_points();
   if (!err.empty()) return err;
   memset(&L, 0, sizeof L);
@@ -629,6 +662,16 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
     err = encode_2d(&L.tmapOut, out_bf16, Cout, p.M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   else
     L.tmapOut = L.tmapB;
+  if (!err.empty()) return err;
+  // residual [M][Cout] bf16, fetched by the epilogue warps with the same 32 x 32 boxes
+  if (residual_bf16) {
+    if (!out_bf16) return "conv: a residual needs a bf16 output";
+    if (mode == kModeGatherC4) return "stem conv: residual inputs are not supported";
+    err = encode_2d(&L.tmapRes, residual_bf16, Cout, p.M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    p.residual = static_cast<const __nv_bfloat16*>(residual_bf16);
+  } else {
+    L.tmapRes = L.tmapB;
+  }
   return err;
 }
 

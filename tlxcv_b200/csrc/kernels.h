@@ -44,7 +44,7 @@ struct ConvKernelParams {
 };
 
 struct TcConvLaunch {
-  CUtensorMap tmapA, tmapB, tmapOut;
+  CUtensorMap tmapA, tmapB, tmapOut, tmapRes;
   ConvKernelParams p;
   int mode, block_n, grid, threads, smem;
 };
@@ -52,7 +52,7 @@ struct TcConvLaunch {
 // Encodes the TMA descriptors and picks tile shape; returns an empty string or an error message.
 std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
                             int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
-                            int pad, int dil, int groups, int force_block_n, void* out_bf16);
+                            int pad, int dil, int groups, int force_block_n, void* out_bf16, const void* residual_bf16);
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
 cudaError_t tc_conv_set_attributes();
 // number of K elements per output channel in the packed weight matrix for this geometry

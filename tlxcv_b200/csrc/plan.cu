@@ -250,8 +250,19 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
     if (out.d.role != TLXCV_ROLE_INTERNAL) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: bf16 output must be an internal tensor");
     out_bf16 = p->arena + out.offset;
   }
+  const void* res_bf16 = nullptr;
+  if (d.in1 >= 0) {
+    const TensorRt& r = p->tensors[d.in1];
+    if (r.d.role != TLXCV_ROLE_INTERNAL || r.d.dtype != TLXCV_ACT)
+      return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: the residual must be an internal activation tensor");
+    res_bf16 = p->arena + r.offset;
+  }
+  if (d.act2 != TLXCV_ACT_NONE && d.act2 != TLXCV_ACT_RELU)
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: only ReLU (or nothing) may follow the residual add on the tensor-core path");
+  if (d.act2 != TLXCV_ACT_NONE && d.in1 < 0)
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: a second activation without a residual add");
   std::string err = tc_conv_prepare(op.tc, ctx->sm_count, act_in, N, H, W, C, in.cs, w, Ktot, K, R, S, stride, pad, dil,
-                                    groups, force_bn, out_bf16);
+                                    groups, force_bn, out_bf16, res_bf16);
   if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
   ConvKernelParams& kp = op.tc.p;
   kp.scale = op.scale, kp.shift = op.shift;
@@ -286,8 +297,7 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
       break;
     case kImplTcConv: {
       TcConvLaunch L = op.tc;
-      L.p.out = pout;
-      L.p.residual = static_cast<const __nv_bfloat16*>(pres);
+      L.p.out = pout;  // only read by fp32-output (logits) launches; bf16 tensors go through the baked TMA maps
       TLX_CUDA(ctx, tc_conv_launch(L, st));
       break;
     }
