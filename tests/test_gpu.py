@@ -1,0 +1,325 @@
+"""Parity tests proper (-m gpu): the CUDA path, called through the C-ABI library, against the CPU
+oracle on the same seeded inputs and against the committed golden fixtures.
+
+Tolerances (north_star): bf16 mode max-abs logit error <= 1e-2 and identical top-1 (where the
+oracle's own top-1/top-2 margin exceeds the error bound); fp32 validation mode <= 1e-4.
+Single fused layers are checked against fp32 math on bf16-rounded operands: the only differences
+left are accumulation order and the final bf16 rounding, <= 2^-7 of the output scale.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _need_b200():
+    if not torch.cuda.is_available():
+        pytest.fail("-m gpu tests need a B200: tlxcv_b200 has no CPU fallback")
+    from tlxcv_b200 import runtime
+
+    runtime.context(0)      # raises unless libtlxcv_b200.so loaded and the device is sm_100
+
+
+def _loaded_native_library():
+    with open("/proc/self/maps") as f:
+        return any("libtlxcv_b200.so" in line for line in f)
+
+
+def test_native_library_is_the_thing_that_runs():
+    from tlxcv_b200 import models, runtime
+
+    m = models.resnet18().cuda().set_eval()
+    y = m(torch.randn(1, 3, 64, 64, device="cuda"))
+    assert y.shape == (1, 1000) and _loaded_native_library()
+    plan = next(iter(m.__dict__["_b200_plans"].values()))[0]
+    kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
+    assert any(k.startswith("conv_tcgen05_gatherc4") for k in kernels)
+    assert any(k.startswith("conv_tcgen05_im2col") for k in kernels)
+    assert plan.num_launches == len(kernels)
+    assert runtime.context(0).sm_count >= 100
+
+
+# ------------------------------------------------------------------------------------------------
+# single fused layers
+# ------------------------------------------------------------------------------------------------
+def _layer_case(n, cin, hw, cout, k, stride, pad, groups=1, act=None, res=False, act2=None, prec="bf16", bias=False,
+                bn=True, seed=0):
+    from tlxcv_b200 import nn, runtime
+
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn(n, cin, hw, hw, generator=g)
+    w = torch.randn(cout, cin // groups, k, k, generator=g) * (2.0 / (cin // groups * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1 if bias else None
+    gamma, beta = 0.75 + 0.5 * torch.rand(cout, generator=g), torch.randn(cout, generator=g) * 0.1
+    mean, var = torch.randn(cout, generator=g) * 0.1, 0.75 + 0.5 * torch.rand(cout, generator=g)
+    po = (hw + 2 * pad - k) // stride + 1
+    r = torch.randn(n, cout, po, po, generator=g) if res else None
+    acts = {"relu": nn.ReLU, "relu6": nn.ReLU6, "leaky": lambda: nn.LeakyReLU(0.1)}
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.GroupConv2d(in_channels=cin, out_channels=cout, kernel_size=k, stride=stride, padding=pad,
+                                       n_group=groups, b_init="constant" if bias else None)
+            self.bn = nn.BatchNorm2d(num_features=cout) if bn else None
+            self.a1 = acts[act]() if act else None
+            self.a2 = acts[act2]() if act2 else None
+
+        def forward(self, x, r=None):
+            y = self.conv(x)
+            y = self.bn(y) if self.bn is not None else y
+            y = self.a1(y) if self.a1 is not None else y
+            y = y + r if r is not None else y
+            return self.a2(y) if self.a2 is not None else y
+
+    net = Net()
+    sd = {"conv.filters": w}
+    if bias:
+        sd["conv.biases"] = b
+    if bn:
+        sd.update({"bn.beta": beta, "bn.gamma": gamma, "bn.moving_mean": mean, "bn.moving_var": var})
+    net.load_state_dict(sd)
+    net = net.cuda().set_eval()
+    precision = runtime.PREC_F32 if prec == "f32" else runtime.PREC_BF16
+    args = (x.cuda(),) if r is None else (x.cuda(), r.cuda())
+    plan, _, flat = runtime.get_plan(net, args, {}, precision=precision)
+    out = plan.run(flat, graph=False)[0].cpu()
+
+    q = (lambda t: t) if prec == "f32" else (lambda t: t.bfloat16().float())
+    y = F.conv2d(q(x), q(w), b, stride, pad, 1, groups)
+    if bn:
+        y = F.batch_norm(y, mean, var, gamma, beta, False, 0.0, 1e-5)
+    fa = {None: lambda t: t, "relu": F.relu, "relu6": F.relu6, "leaky": lambda t: F.leaky_relu(t, 0.1)}
+    y = fa[act](y)
+    if r is not None:
+        y = y + q(r)
+    y = fa[act2](y)
+    scale = max(1.0, float(y.abs().max()))
+    tol = 2e-4 * scale if prec == "f32" else 2.0 ** -7 * scale
+    kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
+    return float((out - y).abs().max()), tol, kernels, bool(torch.isfinite(out).all())
+
+
+LAYERS = {
+    # name: (kwargs, expected kernel prefix)
+    "gemm_1x1": (dict(n=2, cin=64, hw=16, cout=64, k=1, stride=1, pad=0, bn=False), "conv_tcgen05_tiled"),
+    "gemm_1x1_bn_relu_k256": (dict(n=3, cin=256, hw=14, cout=128, k=1, stride=1, pad=0, act="relu"), "conv_tcgen05_tiled"),
+    "gemm_1x1_residual_relu": (dict(n=2, cin=128, hw=14, cout=512, k=1, stride=1, pad=0, res=True, act2="relu"),
+                               "conv_tcgen05_tiled"),
+    "gemm_1x1_bias_no_bn": (dict(n=2, cin=64, hw=8, cout=72, k=1, stride=1, pad=0, bn=False, bias=True), "conv_tcgen05_tiled"),
+    "gemm_m_tail_49px": (dict(n=1, cin=64, hw=7, cout=256, k=1, stride=1, pad=0, act="relu"), "conv_tcgen05_tiled"),
+    "gemm_c_tails_24_144": (dict(n=2, cin=24, hw=12, cout=144, k=1, stride=1, pad=0, act="relu6"), "conv_tcgen05_tiled"),
+    "gemm_cout_24": (dict(n=2, cin=96, hw=12, cout=24, k=1, stride=1, pad=0), "conv_tcgen05_tiled"),
+    "im2col_3x3": (dict(n=2, cin=64, hw=14, cout=64, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col"),
+    "im2col_3x3_s2": (dict(n=2, cin=128, hw=28, cout=128, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_im2col"),
+    "im2col_3x3_7x7_images_wrap": (dict(n=5, cin=256, hw=7, cout=256, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col"),
+    "im2col_1x1_s2_downsample": (dict(n=2, cin=256, hw=14, cout=512, k=1, stride=2, pad=0), "conv_tcgen05_im2col"),
+    "im2col_3x3_c32_leaky": (dict(n=2, cin=32, hw=20, cout=64, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col"),
+    "im2col_leaky_then_residual": (dict(n=2, cin=64, hw=10, cout=128, k=3, stride=1, pad=1, act="leaky", res=True),
+                                   "conv_tcgen05_im2col"),
+    "im2col_odd_size_19": (dict(n=1, cin=64, hw=19, cout=128, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col"),
+    "grouped_g32_c128": (dict(n=2, cin=128, hw=14, cout=128, k=3, stride=1, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
+    "grouped_g32_c256_s2": (dict(n=2, cin=256, hw=14, cout=256, k=3, stride=2, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
+    "grouped_g32_c1024": (dict(n=1, cin=1024, hw=7, cout=1024, k=3, stride=1, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
+    "depthwise_s1": (dict(n=2, cin=32, hw=14, cout=32, k=3, stride=1, pad=1, groups=32, act="relu6"), "dwconv"),
+    "depthwise_s2_c96": (dict(n=2, cin=96, hw=15, cout=96, k=3, stride=2, pad=1, groups=96, act="relu6"), "dwconv"),
+    "stem_7x7_s2": (dict(n=2, cin=3, hw=64, cout=64, k=7, stride=2, pad=3, act="relu"), "conv_tcgen05_gatherc4"),
+    "stem_3x3_s2_c32": (dict(n=2, cin=3, hw=32, cout=32, k=3, stride=2, pad=1, act="relu6"), "conv_tcgen05_gatherc4"),
+    "stem_3x3_s1_leaky": (dict(n=2, cin=3, hw=24, cout=32, k=3, stride=1, pad=1, act="leaky"), "conv_tcgen05_gatherc4"),
+    "f32_1x1": (dict(n=2, cin=64, hw=14, cout=64, k=1, stride=1, pad=0, act="relu", prec="f32"), "conv_direct_f32"),
+    "f32_3x3_residual": (dict(n=2, cin=32, hw=9, cout=32, k=3, stride=1, pad=1, act="leaky", res=True, prec="f32"), "conv_direct_f32"),
+    "f32_stem": (dict(n=2, cin=3, hw=32, cout=64, k=7, stride=2, pad=3, act="relu", prec="f32"), "conv_direct_f32"),
+    "f32_depthwise": (dict(n=2, cin=32, hw=12, cout=32, k=3, stride=2, pad=1, groups=32, act="relu6", prec="f32"), "conv_direct_f32"),
+    "f32_grouped": (dict(n=2, cin=128, hw=8, cout=128, k=3, stride=1, pad=1, groups=32, act="relu", prec="f32"), "conv_direct_f32"),
+}
+
+
+@pytest.mark.parametrize("name", sorted(LAYERS))
+def test_fused_layer_matches_reference_math(name):
+    kw, kernel = LAYERS[name]
+    err, tol, kernels, finite = _layer_case(**kw, seed=sum(map(ord, name)))
+    assert any(k.startswith(kernel) for k in kernels), kernels
+    assert finite and err <= tol, f"{name}: max err {err:.4g} > {tol:.4g}"
+
+
+def test_maxpool_gap_linear_argmax_small():
+    """Stem + MaxPool2d(3,2,1) + GAP + Linear + argmax on their own (fp32 mode: exact semantics, incl. -inf pool padding)."""
+    import tlxcv_b200 as tlx
+    from tlxcv_b200 import nn, runtime
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.GroupConv2d(in_channels=3, out_channels=64, kernel_size=3, stride=1, padding=1, b_init=None)
+            self.bn = nn.BatchNorm2d(num_features=64)
+            self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+            self.gap = nn.AdaptiveAvgPool2d(1)
+            self.fc = nn.Linear(in_features=64, out_features=40)
+
+        def forward(self, x):
+            y = self.pool(self.bn(self.conv(x)))
+            logits = self.fc(tlx.flatten(self.gap(y), 1))
+            return logits, tlx.argmax(logits, axis=-1), y
+
+    net = Net()
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for p_ in net.parameters():
+            p_.copy_(torch.randn(p_.shape, generator=g) * 0.3)
+        net.bn.moving_var.copy_(0.5 + torch.rand(64, generator=g))
+        net.bn.gamma.copy_(0.05 + 0.05 * torch.rand(64, generator=g))
+        net.bn.beta.copy_(-3.0 + 0.1 * torch.randn(64, generator=g))   # all-negative maps: zero padding in the pool would show up as 0
+    x = torch.randn(3, 3, 13, 13, generator=g)
+    sd = {k: v.clone() for k, v in net.state_dict().items()}
+    net = net.cuda().set_eval()
+    plan, structure, flat = runtime.get_plan(net, (x.cuda(),), {}, precision=runtime.PREC_F32)
+    logits, pred, y = [t.cpu() for t in plan.run(flat, graph=False)]
+    c = F.conv2d(x, sd["conv.filters"], None, 1, 1)
+    c = F.batch_norm(c, sd["bn.moving_mean"], sd["bn.moving_var"], sd["bn.gamma"], sd["bn.beta"], False, 0.0, 1e-5)
+    yr = F.max_pool2d(c, 3, 2, 1)
+    lr = F.adaptive_avg_pool2d(yr, 1).flatten(1) @ sd["fc.weights"] + sd["fc.biases"]
+    assert float(yr.max()) < 0
+    assert float((y - yr).abs().max()) <= 1e-5
+    assert float((logits - lr).abs().max()) <= 1e-4
+    assert torch.equal(pred, lr.argmax(1))
+
+
+# ------------------------------------------------------------------------------------------------
+# whole models vs the oracle and the golden fixtures
+# ------------------------------------------------------------------------------------------------
+def _model_case(name, n, size, prec, golden=False):
+    from oracle import restated
+    from tlxcv_b200 import models, runtime
+    from tlxcv_b200.testing import seeded_state_dict, synthetic_images
+
+    model = models.REGISTRY[name]()
+    sd = seeded_state_dict(model.state_dict(), name)
+    model.load_state_dict(sd)
+    model = model.cuda().set_eval()
+    x = synthetic_images(n, size)
+    det = name == "darknet53_det"
+    if golden:
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+        assert (int(g["n"]), int(g["size"])) == (n, size)
+        refs = [torch.from_numpy(g[k]) for k in sorted(k for k in g.files if k.startswith("out"))]
+    else:
+        ref = restated.forward(name, sd, {"images": x} if det else x)
+        refs = ref if isinstance(ref, list) else [ref]
+    precision = runtime.PREC_F32 if prec == "f32" else runtime.PREC_BF16
+    args = ({"images": x.cuda()},) if det else (x.cuda(),)
+    plan, _, flat = runtime.get_plan(model, args, {}, precision=precision)
+    eager = [o.cpu() for o in plan.run(flat, graph=False)]
+    graphed = [o.cpu() for o in plan.run(flat, graph=True)]
+    again = [o.cpu() for o in plan.run(flat, graph=True)]
+    for a, b, c in zip(eager, graphed, again):
+        assert torch.equal(a, b) and torch.equal(a, c), "CUDA-graph replay differs from the stream launch"
+    return eager, refs
+
+
+CLS = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls"]
+
+
+@pytest.mark.parametrize("name", CLS)
+def test_classifier_bf16_vs_golden_reference_outputs(name):
+    """Golden fixtures = outputs of the reference's own model files (tests/golden/make_golden.py)."""
+    n = 4 if name == "resnet50" else 2
+    outs, refs = _model_case(name, n, 224, "bf16", golden=True)
+    y, r = outs[0], refs[0]
+    err = float((y - r).abs().max())
+    top2 = r.topk(2, dim=1).values
+    margin = top2[:, 0] - top2[:, 1]
+    assert err <= 1e-2, f"{name}: max-abs logit error {err:.3e} (logit std {float(r.std()):.3f})"
+    # identical top-1 wherever the reference's own decision margin exceeds twice the error bound
+    agree = y.argmax(1) == r.argmax(1)
+    assert bool((agree | (margin < 2e-2)).all())
+
+
+@pytest.mark.parametrize("name", ["resnet50", "mobilenet_v2", "resnext50_32x4d"])
+def test_classifier_fp32_validation_mode(name):
+    outs, refs = _model_case(name, 2, 96, "f32")
+    err = float((outs[0] - refs[0]).abs().max())
+    assert err <= 1e-4, f"{name}: fp32 validation mode max-abs error {err:.3e}"
+    assert torch.equal(outs[0].argmax(1), refs[0].argmax(1))
+
+
+def test_darknet53_detection_backbone_feature_maps():
+    outs, refs = _model_case("darknet53_det", 1, 64, "bf16", golden=True)
+    assert [tuple(o.shape) for o in outs] == [(1, 256, 8, 8), (1, 512, 4, 4), (1, 1024, 2, 2)]
+    for o, r in zip(outs, refs):
+        rel = float((o - r).abs().max()) / float(r.abs().max())
+        assert rel <= 0.03, rel                                   # bf16 through 52 layers, feature scale ~2-7
+    outs32, refs32 = _model_case("darknet53_det", 1, 64, "f32")
+    for o, r in zip(outs32, refs32):
+        assert float((o - r).abs().max()) <= 1e-4 * max(1.0, float(r.abs().max()))
+
+
+def test_darknet53_608_shapes_and_dict_input():
+    from tlxcv_b200 import models
+    from tlxcv_b200.testing import seeded_state_dict
+
+    m = models.DarkNet()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), "darknet53_det"))
+    m = m.cuda().set_eval()
+    feats = m({"images": torch.randn(1, 3, 608, 608, device="cuda")})
+    assert [tuple(f.shape) for f in feats] == [(1, 256, 76, 76), (1, 512, 38, 38), (1, 1024, 19, 19)]
+    assert all(bool(torch.isfinite(f).all()) for f in feats)
+
+
+# ------------------------------------------------------------------------------------------------
+# full-size, size-independent properties (BASELINE.json config: ResNet-50 bs256 224x224)
+# ------------------------------------------------------------------------------------------------
+def test_resnet50_bs256_batch_invariance_and_predict():
+    """Images are independent in eval mode: image i's logits must not depend on the batch it rides in,
+    bit for bit (same kernels, same per-row arithmetic), and predict() == argmax(logits)."""
+    from tlxcv_b200 import models, tasks
+    from tlxcv_b200.testing import seeded_state_dict, synthetic_images
+
+    m = models.resnet50()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), "resnet50"))
+    m = m.cuda().set_eval()
+    x = synthetic_images(32, 224, seed=9).repeat(8, 1, 1, 1).cuda()     # 256 images, 8 copies of 32
+    full = m(x)
+    assert full.shape == (256, 1000)
+    assert torch.equal(full[:32], full[32:64]) and torch.equal(full[:32], full[224:])   # same image -> same logits
+    part = m(x[:32].contiguous())
+    err = float((part - full[:32]).abs().max())
+    assert err <= 2e-3, err          # other tile shapes may be picked for M=32 images: same math, other summation order
+    pred = tasks.ImageClassification(m).predict(x)
+    assert pred.dtype == torch.int64 and torch.equal(pred, full.argmax(1))
+
+
+def test_weight_update_rebuilds_the_plan():
+    from tlxcv_b200 import models
+
+    m = models.resnet18().cuda().set_eval()
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    a = m(x)
+    with torch.no_grad():
+        m.fc.biases.add_(1.0)
+    b = m(x)
+    assert float((b - a - 1.0).abs().max()) < 1e-5
+
+
+def test_host_pipeline_matches_device_path():
+    from tlxcv_b200 import models
+    from tlxcv_b200.pipeline import HostPipeline
+    from tlxcv_b200.testing import seeded_state_dict, synthetic_images
+
+    m = models.resnet18()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), "resnet18"))
+    m = m.cuda().set_eval()
+    xs = [synthetic_images(4, 96, seed=s).pin_memory() for s in range(3)]
+    outs = [torch.empty(4, 1000).pin_memory() for _ in range(3)]
+    pipe = HostPipeline(m, (4, 3, 96, 96))
+    for xi, oi in zip(xs, outs):
+        pipe.submit(xi, oi)
+    pipe.synchronize()
+    for xi, oi in zip(xs, outs):
+        assert torch.equal(oi, m(xi.cuda()).cpu())

@@ -201,7 +201,10 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   const double flops = 2.0 * M * K * Cg * R * S;
   const double wbytes = static_cast<double>(K) * Cg * R * S * (p->f32 ? 4 : 2);
   const double obytes = M * K * (out.d.dtype == TLXCV_F32 ? 4 : p->esize);
-  const double bytes = static_cast<double>(N) * H * W * C * p->esize + wbytes + obytes + (d.in1 >= 0 ? M * K * p->esize : 0);
+  // input pixels a filter actually touches (a 1x1 stride-2 conv reads a quarter of its input)
+  const double th = R >= stride ? std::min<double>(H, (P - 1.0) * stride + (R - 1) * dil + 1) : static_cast<double>(P) * R;
+  const double tw = S >= stride ? std::min<double>(W, (Q - 1.0) * stride + (S - 1) * dil + 1) : static_cast<double>(Q) * S;
+  const double bytes = static_cast<double>(N) * th * tw * C * p->esize + wbytes + obytes + (d.in1 >= 0 ? M * K * p->esize : 0);
 
   if (p->f32) {
     float* w = nullptr;
