@@ -111,6 +111,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   }
 }
 
+// 8-byte asynchronous global -> shared copy; `valid == false` writes zeros and reads nothing
+__device__ __forceinline__ void cp_async_8_zfill(uint32_t dst, const void* src, bool valid) {
+  const uint32_t n = valid ? 8u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(dst), "l"(src), "r"(n) : "memory");
+}
+
 // generic-proxy smem writes -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

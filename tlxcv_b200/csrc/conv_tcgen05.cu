@@ -20,6 +20,7 @@
 // w8-11 gather producers (kModeGatherC4 only).
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -34,8 +35,8 @@ constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
 constexpr int kEpiWarps = 8;                    // warps 2..9
 constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
-constexpr int kRing = 4;                        // per epilogue warp: ring of 4 x (32 rows x 64 B) SWIZZLE_64B buffers
-constexpr int kStagingBytes = kEpiWarps * kRing * 2048;
+constexpr int kMaxRing = 4;                     // per epilogue warp: ring of 2 or 4 (32 rows x 64 B) SWIZZLE_64B buffers
+constexpr int kSmemLimit = 232448;              // 227 KB of dynamic shared memory per CTA
 constexpr int kScaleCacheBytes = 2 * 256 * 4;   // [scale | shift] of one N tile (used when the layer has one N tile)
 constexpr int kBarrierBytes = 512;              // pipeline barriers + kEpiWarps * kRing residual barriers
 constexpr int kMaxStages = 8;
@@ -46,9 +47,18 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = BLOCK_N == 256 ? 3 : (BLOCK_N == 128 ? 5 : 6);
   static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: a power of two >= 32
-  static constexpr int kSmem = kStages * kStageBytes + kStagingBytes + kScaleCacheBytes + kBarrierBytes;
+  // smem layout: [stages x (A | B)] [8 warps x ring x 2 KB] [scale cache] [barriers]; the ring depth
+  // and therefore the stage count are chosen per layer (deep ring for residual / HBM-bound layers,
+  // more operand stages for MMA-bound ones)
+  static constexpr int staging_bytes(int ring) { return kEpiWarps * ring * 2048; }
+  static constexpr int stages_for(int ring) {
+    const int n = (kSmemLimit - staging_bytes(ring) - kScaleCacheBytes - kBarrierBytes) / kStageBytes;
+    return n > kMaxStages ? kMaxStages : n;
+  }
+  static constexpr int smem_bytes(int ring) {
+    return stages_for(ring) * kStageBytes + staging_bytes(ring) + kScaleCacheBytes + kBarrierBytes;
+  }
 };
 
 struct PipeState {
@@ -88,6 +98,7 @@ struct EpiArgs {
   const CUtensorMap* tmap_res;
   int M, Cout, n_tiles, num_tiles, first_tile, tile_stride;
   float alpha1, alpha2;
+  int ablate;
 };
 
 template <int ACT>
@@ -105,8 +116,9 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // items ahead; each lane reads ITS row of the buffer, computes, and writes its output row back into
 // the same buffer, which one TMA store then drains.  No per-element global addressing, no
 // predicates: TMA clips the M and C_out tails.
-template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32>
+template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing>
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
+  static_assert(!RES || kRing == 4, "the residual prefetch runs three items ahead");
   constexpr int kCpw = (BLOCK_N / 32) / 2;  // chunks per warp per tile
   const int c_first = cgroup * kCpw;
   const int swz_own = (lane >> 1) & 3;
@@ -149,7 +161,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     const int n_my = min(kCpw, max(0, (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
-    if (n_my == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);  // nothing to read: release at once
+    if (n_my == 0 && lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);  // nothing to read: release at once
 #pragma unroll 1
     for (int ci = 0; ci < n_my; ++ci, ++it) {
       const int chunk = c_first + ci;
@@ -161,14 +173,21 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         mbar_wait(a.res_bar + slot * 8, (it / kRing) & 1);  // residual chunk has landed in the ring slot
       } else if (!F32) {
         // the TMA store that used this slot kRing items ago must have finished reading it
-        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        if (lane == 0) {
+          if (kRing == 4)
+            asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+          else
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        }
         __syncwarp();
       }
       tmem_ld_wait();
       if (ci == n_my - 1) {
         // this warp's last read of the accumulator: hand the TMEM buffer back to the MMA warp early
+        // (one arrival per warp: 256 same-address smem atomics per tile were a measurable cost)
         tcgen05_fence_before();
-        mbar_arrive(a.tmem_empty_bar + acc * 8);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);
       }
       float f[32];
       if (a.sc_cache != nullptr) {
@@ -228,7 +247,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
       __syncwarp();
       if (lane == 0) {
-        tma_store_2d(a.tmap_out, a.ring + slot * 2048, cbase, m0);
+        if (!(a.ablate & 2)) tma_store_2d(a.tmap_out, a.ring + slot * 2048, cbase, m0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (RES) {
           // refill the slot of item it+3 (== the slot item it-1 used): every store but the one just
@@ -256,15 +275,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   // that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
-  uint8_t* staging = smem + C::kStages * C::kStageBytes;
-  float* sc_cache = reinterpret_cast<float*>(staging + kStagingBytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + kStagingBytes + kScaleCacheBytes);
+  const int n_stages = p.stages, ring = p.ring;
+  const int staging_bytes = kEpiWarps * ring * 2048;
+  uint8_t* staging = smem + n_stages * C::kStageBytes;
+  float* sc_cache = reinterpret_cast<float*>(staging + staging_bytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + kScaleCacheBytes);
   uint64_t* full_bar = bars;                       // [kStages]  operands landed
   uint64_t* empty_bar = bars + kMaxStages;         // [kStages]  MMAs that read the stage retired
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]        accumulator complete
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;    // [2]        accumulator drained by the epilogue
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-  uint64_t* res_bar = bars + 2 * kMaxStages + 8;   // [kEpiWarps][kRing] residual chunk landed
+  uint64_t* res_bar = bars + 2 * kMaxStages + 8;   // [kEpiWarps][kMaxRing] residual chunk landed
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -274,15 +295,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     if (MODE != kModeGatherC4) tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
     if (!p.out_f32) tma_prefetch_desc(&tmapOut);
-    for (int i = 0; i < C::kStages; ++i) {
+    for (int i = 0; i < n_stages; ++i) {
       mbar_init(smem_u32(&full_bar[i]), MODE == kModeGatherC4 ? 1 + kGatherWarps * 32 : 1);
       mbar_init(smem_u32(&empty_bar[i]), 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), kEpiWarps * 32);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), kEpiWarps);  // one arrival per epilogue warp
     }
-    for (int i = 0; i < kEpiWarps * kRing; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    for (int i = 0; i < kEpiWarps * kMaxRing; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     if (!p.out_f32 && p.residual != nullptr) tma_prefetch_desc(&tmapRes);
     fence_barrier_init();
   }
@@ -334,7 +355,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             }
           }
           tma_load_2d(a_dst + kABytes, &tmapB, bar, kb * kBlockK, n0);
-          ps.advance(C::kStages);
+          ps.advance(n_stages);
         }
       }
     }
@@ -357,10 +378,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (!(p.ablate & 4)) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[ps.stage]));  // frees the smem stage when these MMAs retire
-          ps.advance(C::kStages);
+          ps.advance(n_stages);
         }
         umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator ready for the epilogue
         if (++acc == 2) {
@@ -376,8 +397,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.tmem_base = tmem_base;
     a.tmem_full_bar = smem_u32(tmem_full_bar);
     a.tmem_empty_bar = smem_u32(tmem_empty_bar);
-    a.ring = smem_u32(staging + (warp - 2) * (kRing * 2048));
-    a.res_bar = smem_u32(res_bar + (warp - 2) * kRing);
+    a.ring = smem_u32(staging + (warp - 2) * (ring * 2048));
+    a.res_bar = smem_u32(res_bar + (warp - 2) * kMaxRing);
     a.sc_cache = sc_cached ? sc_cache : nullptr;
     a.scale = p.scale, a.shift = p.shift;
     a.out_f32 = reinterpret_cast<float*>(p.out);
@@ -385,13 +406,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.M = p.M, a.Cout = p.Cout, a.n_tiles = p.n_tiles, a.num_tiles = num_tiles;
     a.first_tile = blockIdx.x, a.tile_stride = gridDim.x;
     a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
+    a.ablate = p.ablate;
     const int lg = warp & 3, cgroup = (warp - 2) >> 2;
     const bool res = kRes && p.residual != nullptr;
-#define TLXCV_EPI(A1)                                                                                       \
-  if (p.out_f32) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, true>(a, lg, cgroup, lane);              \
-  else if (!res) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false>(a, lg, cgroup, lane);             \
-  else if (p.act2 == TLXCV_ACT_RELU) epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_RELU, false>(a, lg, cgroup, lane); \
-  else epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_NONE, false>(a, lg, cgroup, lane);
+#define TLXCV_EPI(A1)                                                                                          \
+  if (p.out_f32) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, true, 2>(a, lg, cgroup, lane);              \
+  else if (!res && ring == 2) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false, 2>(a, lg, cgroup, lane); \
+  else if (!res) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false, 4>(a, lg, cgroup, lane);             \
+  else if (p.act2 == TLXCV_ACT_RELU) epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_RELU, false, 4>(a, lg, cgroup, lane); \
+  else epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_NONE, false, 4>(a, lg, cgroup, lane);
     switch (p.act1) {
       case TLXCV_ACT_RELU: TLXCV_EPI(TLXCV_ACT_RELU) break;
       case TLXCV_ACT_RELU6: TLXCV_EPI(TLXCV_ACT_RELU6) break;
@@ -410,42 +433,58 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     const int r_per_kb = kBlockK / p.KR;
     const int cpr_shift = p.KR == 16 ? 1 : 2;  // log2(16-byte chunks per filter row)
     const int PQ = p.P * p.Q;
+    // Fully asynchronous gather: every tap is an 8-byte cp.async (zero-filled outside the image)
+    // straight into the swizzled A tile, and the stage's full barrier is armed with
+    // cp.async.mbarrier.arrive.noinc, so a thread never waits for its own loads: up to n_stages
+    // K blocks of global latency are in flight per thread, with no registers and no proxy fence
+    // (a fence.proxy.async here is a MEMBAR that would drain the outstanding loads).
+    // Address generation is the cost here (8 taps per thread per K block), so everything that does
+    // not depend on the K block is hoisted: a thread's 4 chunks lie in at most two filter-row slots
+    // (A for chunks 0-1, B for chunks 2-3; A == B when a filter row spans 4 chunks), and the column
+    // offsets / column validity of its 8 taps are per-tile constants.
+    const int slotA = (chalf * 4) >> cpr_shift, slotB = (chalf * 4 + 3) >> cpr_shift;
+    const int jmask = (1 << cpr_shift) - 1;
+    const int Wd = p.W, Hd = p.H, dil = p.dil;
     PipeState ps;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles;
-      const int m = m_tile * kBlockM + t;
+      const int m = (tile / p.n_tiles) * kBlockM + t;
       const bool row_ok = m < p.M;
       const int img = row_ok ? m / PQ : 0;
       const int rem = m - img * PQ;
       const int op = rem / p.Q, oq = rem - op * p.Q;
       const int ih0 = op * p.stride - p.pad, iw0 = oq * p.stride - p.pad;
-      const uint2* img_base = reinterpret_cast<const uint2*>(p.in_c4) + static_cast<size_t>(img) * p.H * p.W;
+      const uint2* img_base = reinterpret_cast<const uint2*>(p.in_c4) + static_cast<size_t>(img) * Hd * Wd;
+      int woff[8];
+      uint32_t okw = 0;  // bit 2u: first tap of chunk u is inside the filter and the image row; bit 2u+1: second tap
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = (chalf * 4 + u) & jmask;
+        const int s0 = 2 * j, s1 = s0 + 1;
+        const int w0 = iw0 + s0 * dil, w1 = w0 + dil;
+        woff[2 * u] = w0, woff[2 * u + 1] = w1;
+        if (row_ok && s0 < p.S && w0 >= 0 && w0 < Wd) okw |= 1u << (2 * u);
+        if (row_ok && s1 < p.S && w1 >= 0 && w1 < Wd) okw |= 1u << (2 * u + 1);
+      }
       for (int kb = 0; kb < p.num_kb; ++kb) {
-        uint2 lo[4], hi[4];
-#pragma unroll
-        for (int u = 0; u < 4; ++u) {
-          const int chunk = chalf * 4 + u;
-          const int slot = chunk >> cpr_shift, j = chunk & ((1 << cpr_shift) - 1);
-          const int r = kb * r_per_kb + slot;
-          const int ih = ih0 + r * p.dil;
-          const bool rok = row_ok && r < p.R && ih >= 0 && ih < p.H;
-          const uint2* rowp = img_base + static_cast<size_t>(rok ? ih : 0) * p.W;
-          const int s0 = 2 * j, s1 = 2 * j + 1;
-          const int w0 = iw0 + s0 * p.dil, w1 = iw0 + s1 * p.dil;
-          lo[u] = make_uint2(0, 0), hi[u] = make_uint2(0, 0);
-          if (rok && s0 < p.S && w0 >= 0 && w0 < p.W) lo[u] = __ldg(rowp + w0);
-          if (rok && s1 < p.S && w1 >= 0 && w1 < p.W) hi[u] = __ldg(rowp + w1);
-        }
+        const int rA = kb * r_per_kb + slotA, rB = kb * r_per_kb + slotB;
+        const int ihA = ih0 + rA * dil, ihB = ih0 + rB * dil;
+        const bool okA = rA < p.R && ihA >= 0 && ihA < Hd, okB = rB < p.R && ihB >= 0 && ihB < Hd;
+        const uint2* rowA = img_base + static_cast<size_t>(okA ? ihA : 0) * Wd;
+        const uint2* rowB = img_base + static_cast<size_t>(okB ? ihB : 0) * Wd;
         mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
-        uint8_t* a_row = smem + ps.stage * C::kStageBytes + t * 128;
+        const uint32_t a_row = smem_u32(smem + ps.stage * C::kStageBytes + t * 128);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-          const int chunk = chalf * 4 + u;
-          *reinterpret_cast<uint4*>(a_row + ((chunk ^ (t & 7)) << 4)) = make_uint4(lo[u].x, lo[u].y, hi[u].x, hi[u].y);
+          const uint2* rowp = u < 2 ? rowA : rowB;
+          const bool rok = u < 2 ? okA : okB;
+          const bool ok0 = rok && ((okw >> (2 * u)) & 1u), ok1 = rok && ((okw >> (2 * u + 1)) & 1u);
+          const uint32_t dst = a_row + (((chalf * 4 + u) ^ (t & 7)) << 4);
+          if (p.ablate & 1) continue;
+          cp_async_8_zfill(dst, ok0 ? rowp + woff[2 * u] : img_base, ok0);
+          cp_async_8_zfill(dst + 8, ok1 ? rowp + woff[2 * u + 1] : img_base, ok1);
         }
-        fence_proxy_async_smem();  // make the generic-proxy stores visible to tcgen05.mma's smem reads
-        mbar_arrive(smem_u32(&full_bar[ps.stage]));
-        ps.advance(C::kStages);
+        asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full_bar[ps.stage])) : "memory");
+        ps.advance(n_stages);
       }
     }
   }
@@ -539,11 +578,14 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
 template <int BLOCK_N, int MODE>
 cudaError_t set_attr_t() {
   return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              Cfg<BLOCK_N>::kSmem);
+                              std::max(Cfg<BLOCK_N>::smem_bytes(2), Cfg<BLOCK_N>::smem_bytes(4)));
 }
 
-int smem_for(int block_n) {
-  return block_n == 256 ? Cfg<256>::kSmem : (block_n == 128 ? Cfg<128>::kSmem : Cfg<64>::kSmem);
+int smem_for(int block_n, int ring) {
+  return block_n == 256 ? Cfg<256>::smem_bytes(ring) : (block_n == 128 ? Cfg<128>::smem_bytes(ring) : Cfg<64>::smem_bytes(ring));
+}
+int stages_for(int block_n, int ring) {
+  return block_n == 256 ? Cfg<256>::stages_for(ring) : (block_n == 128 ? Cfg<128>::stages_for(ring) : Cfg<64>::stages_for(ring));
 }
 
 }  // namespace
@@ -639,7 +681,13 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   L.mode = mode;
   L.block_n = block_n;
   L.threads = mode == kModeGatherC4 ? kThreadsGather : kThreadsBase;
-  L.smem = smem_for(block_n);
+  // residual layers and short-K (HBM / epilogue bound) layers get the deep store ring; long-K
+  // (MMA bound) layers trade it for one more operand stage
+  if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only: results are wrong
+  p.ring = (residual_bf16 != nullptr || p.num_kb <= 8) ? 4 : 2;
+  if (!out_bf16) p.ring = 2;
+  p.stages = stages_for(block_n, p.ring);
+  L.smem = smem_for(block_n, p.ring);
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   L.grid = static_cast<int>(std::min<long long>(tiles, sm_count));
 

@@ -166,9 +166,10 @@ __global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __rest
 // ------------------------------------------------------------------------------------------------
 // pooling
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int KS>  // KS = compile-time window (3) or 0 for a runtime window
 __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C8, int P, int Q,
-                                    int k, int stride, int pad, size_t total) {
+                                    int k_rt, int stride, int pad, size_t total) {
+  const int k = KS > 0 ? KS : k_rt;
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int c8 = static_cast<int>(idx % C8);
@@ -181,9 +182,11 @@ __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
 #pragma unroll
   for (int i = 0; i < 8; ++i) m[i] = -FLT_MAX;  // padding behaves as -inf (F.max_pool2d)
   const int h0 = pp * stride - pad, w0 = q * stride - pad;
+#pragma unroll
   for (int r = 0; r < k; ++r) {
     const int h = h0 + r;
     if (h < 0 || h >= H) continue;
+#pragma unroll
     for (int s = 0; s < k; ++s) {
       const int w = w0 + s;
       if (w < 0 || w >= W) continue;
@@ -407,9 +410,11 @@ cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C,
   if (C % 8) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
   if (is_f32)
-    maxpool_nhwc_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+    maxpool_nhwc_kernel<float, 0><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+  else if (k == 3)
+    maxpool_nhwc_kernel<__nv_bfloat16, 3><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   else
-    maxpool_nhwc_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+    maxpool_nhwc_kernel<__nv_bfloat16, 0><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   return cudaGetLastError();
 }
 

@@ -41,6 +41,9 @@ struct ConvKernelParams {
   // gather mode
   const __nv_bfloat16* in_c4;
   int R, KR;  // filter height; K elements reserved per filter row (16 or 32)
+  // shared-memory configuration chosen per layer
+  int ablate;  // debug: TLXCV_DEBUG_ABLATE bit mask (timing experiments; 0 in normal operation)
+  int stages, ring;  // operand pipeline stages; epilogue store/residual ring depth per warp (2 or 4)
 };
 
 struct TcConvLaunch {
