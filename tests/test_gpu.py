@@ -40,9 +40,9 @@ def test_native_library_is_the_thing_that_runs():
     assert y.shape == (1, 1000) and _loaded_native_library()
     plan = next(iter(m.__dict__["_b200_plans"].values()))[0]
     kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
-    assert any(k.startswith("conv_tcgen05_gatherc4") for k in kernels)
+    assert any(k.startswith("stem_rowring") and k.endswith("_maxpool") for k in kernels)
     assert any(k.startswith("conv_tcgen05_im2col") for k in kernels)
-    assert plan.num_launches == len(kernels)
+    assert plan.num_launches == len(kernels) - 1          # the max-pool is fused into the stem: one op, no launch
     assert runtime.context(0).sm_count >= 100
 
 
@@ -130,9 +130,13 @@ LAYERS = {
     "grouped_g32_c1024": (dict(n=1, cin=1024, hw=7, cout=1024, k=3, stride=1, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
     "depthwise_s1": (dict(n=2, cin=32, hw=14, cout=32, k=3, stride=1, pad=1, groups=32, act="relu6"), "dwconv"),
     "depthwise_s2_c96": (dict(n=2, cin=96, hw=15, cout=96, k=3, stride=2, pad=1, groups=96, act="relu6"), "dwconv"),
-    "stem_7x7_s2": (dict(n=2, cin=3, hw=64, cout=64, k=7, stride=2, pad=3, act="relu"), "conv_tcgen05_gatherc4"),
-    "stem_3x3_s2_c32": (dict(n=2, cin=3, hw=32, cout=32, k=3, stride=2, pad=1, act="relu6"), "conv_tcgen05_gatherc4"),
-    "stem_3x3_s1_leaky": (dict(n=2, cin=3, hw=24, cout=32, k=3, stride=1, pad=1, act="leaky"), "conv_tcgen05_gatherc4"),
+    "stem_7x7_s2": (dict(n=2, cin=3, hw=64, cout=64, k=7, stride=2, pad=3, act="relu"), "stem_rowring_n64"),
+    "stem_7x7_s2_odd_37": (dict(n=3, cin=3, hw=37, cout=64, k=7, stride=2, pad=3, act="relu"), "stem_rowring_n64"),
+    "stem_3x3_s2_c32": (dict(n=2, cin=3, hw=32, cout=32, k=3, stride=2, pad=1, act="relu6"), "stem_rowring_n32"),
+    "stem_3x3_s1_leaky": (dict(n=2, cin=3, hw=24, cout=32, k=3, stride=1, pad=1, act="leaky"), "stem_rowring_n64_pairs"),
+    "stem_3x3_s1_two_column_tiles": (dict(n=1, cin=3, hw=300, cout=32, k=3, stride=1, pad=1, act="leaky"), "stem_rowring_n64_pairs"),
+    "stem_5x5_s1_c16": (dict(n=2, cin=3, hw=20, cout=16, k=5, stride=1, pad=2, act="relu"), "stem_rowring_n32_pairs"),
+    "stem_3x3_s2_c128_gather_fallback": (dict(n=2, cin=3, hw=20, cout=128, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_gatherc4"),
     "f32_1x1": (dict(n=2, cin=64, hw=14, cout=64, k=1, stride=1, pad=0, act="relu", prec="f32"), "conv_direct_f32"),
     "f32_3x3_residual": (dict(n=2, cin=32, hw=9, cout=32, k=3, stride=1, pad=1, act="leaky", res=True, prec="f32"), "conv_direct_f32"),
     "f32_stem": (dict(n=2, cin=3, hw=32, cout=64, k=7, stride=2, pad=3, act="relu", prec="f32"), "conv_direct_f32"),
@@ -147,6 +151,63 @@ def test_fused_layer_matches_reference_math(name):
     err, tol, kernels, finite = _layer_case(**kw, seed=sum(map(ord, name)))
     assert any(k.startswith(kernel) for k in kernels), kernels
     assert finite and err <= tol, f"{name}: max err {err:.4g} > {tol:.4g}"
+
+
+@pytest.mark.parametrize("hw,neg", [(64, False), (30, False), (224, True)])
+def test_stem_with_fused_maxpool_bf16(hw, neg):
+    """Stem conv + BN (+ReLU) + MaxPool2d(3,2,1) in ONE kernel (the conv map never reaches HBM): must equal
+    the unfused bf16 pipeline bit for bit (max of bf16-rounded values), including the -inf pool padding
+    (all-negative maps: zero padding would show up as 0)."""
+    from tlxcv_b200 import nn, runtime
+
+    g = torch.Generator().manual_seed(hw)
+    x = torch.randn(2, 3, hw, hw, generator=g)
+    w = torch.randn(64, 3, 7, 7, generator=g) * (2.0 / 147) ** 0.5
+    gamma, beta = 0.75 + 0.5 * torch.rand(64, generator=g), torch.randn(64, generator=g) * 0.1 - (30.0 if neg else 0.0)
+    mean, var = torch.randn(64, generator=g) * 0.1, 0.75 + 0.5 * torch.rand(64, generator=g)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.GroupConv2d(in_channels=3, out_channels=64, kernel_size=7, stride=2, padding=3, b_init=None)
+            self.bn = nn.BatchNorm2d(num_features=64)
+            self.act = None if neg else nn.ReLU()
+            self.pool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+
+        def forward(self, x):
+            y = self.bn(self.conv(x))
+            return self.pool(self.act(y) if self.act is not None else y)
+
+    def run():
+        net = Net()
+        net.load_state_dict({"conv.filters": w, "bn.beta": beta, "bn.gamma": gamma, "bn.moving_mean": mean, "bn.moving_var": var})
+        net = net.cuda().set_eval()
+        plan, _, flat = runtime.get_plan(net, (x.cuda(),), {})
+        return plan.run(flat, graph=False)[0].cpu(), [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
+
+    fused, kernels = run()
+    assert "stem_rowring_n64_maxpool" in kernels, kernels
+    os.environ["TLXCV_NO_POOL_FUSION"] = "1"
+    try:
+        unfused, kernels2 = run()
+    finally:
+        del os.environ["TLXCV_NO_POOL_FUSION"]
+    assert "maxpool_nhwc" in kernels2 and "stem_rowring_n64" in kernels2, kernels2
+    assert torch.equal(fused, unfused)
+    os.environ["TLXCV_NO_ROWRING"] = "1"
+    try:
+        gathered, kernels3 = run()
+    finally:
+        del os.environ["TLXCV_NO_ROWRING"]
+    assert any(k.startswith("conv_tcgen05_gatherc4") for k in kernels3), kernels3
+    q = lambda t: t.bfloat16().float()
+    y = F.batch_norm(F.conv2d(q(x), q(w), None, 2, 3), mean, var, gamma, beta, False, 0.0, 1e-5)
+    y = F.max_pool2d(q(y if neg else F.relu(y)), 3, 2, 1)
+    tol = 2.0 ** -7 * max(1.0, float(y.abs().max()))
+    assert fused.shape == y.shape and float((fused - y).abs().max()) <= tol
+    assert float((gathered - y).abs().max()) <= tol
+    if neg:
+        assert float(fused.max()) < 0
 
 
 def test_maxpool_gap_linear_argmax_small():

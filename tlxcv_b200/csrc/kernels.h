@@ -62,6 +62,49 @@ cudaError_t tc_conv_set_attributes();
 int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode);
 int tc_conv_mode(int Cin, int R, int S, int stride, int pad, int groups);
 
+// ---- stem conv (C_in <= 4) as a row-ring implicit GEMM, optional fused 3x3/s2/p1 max-pool ------------
+struct StemGeometry {
+  int pairs;    // stride-1 stems run over pairs of output pixels (GEMM N = 2 * C_out)
+  int block_n;  // GEMM N: 32 or 64
+  int P, Q;     // conv output size
+  int Qw;       // A rows (windows) per output row: Q, or Q/2 in pair mode
+  int pad_l;    // zero columns stored left of each input row (even, >= pad)
+  int xoff;     // window position of filter column 0 (pad_l - pad)
+  int Wp;       // stored row pitch in pixels (input is [N][H][Wp][4] bf16)
+};
+
+struct StemParams {
+  int N, H, P, Qw;
+  int R, sv, pad;
+  int bands, band_rows, q_tiles;
+  int pool, Pp, Qp;
+  const float* scale;  // [block_n] (pair mode: the per-channel values twice)
+  const float* shift;
+  int act;
+  float alpha;
+  __nv_bfloat16* out;  // [N][P][Qw][block_n] == NHWC, or the pooled map [N][Pp][Qp][block_n]
+  int ablate;          // debug: TLXCV_DEBUG_ABLATE_STEM bit mask (timing experiments; 0 in normal operation)
+};
+
+struct StemLaunch {
+  CUtensorMap tmapA, tmapB;
+  StemParams p;
+  int block_n, grid, threads, smem;
+};
+
+// false when the geometry is not one the row-ring kernel covers (the gather path of conv_tcgen05 is used instead)
+bool stem_rowring_geometry(StemGeometry& g, int Cin, int Cout, int H, int W, int R, int S, int stride, int pad, int dil,
+                           int groups);
+std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry& g, const __nv_bfloat16* in_padded, int N,
+                                 int H, int R, int stride, int pad, const __nv_bfloat16* packed_w, void* out, int pool,
+                                 int Pp, int Qp);
+cudaError_t stem_rowring_launch(const StemLaunch& L, cudaStream_t st);
+cudaError_t stem_rowring_set_attributes();
+cudaError_t pack_stem_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cin, int R, int S, const StemGeometry& g,
+                              cudaStream_t st);
+// NCHW fp32 (C <= 4) -> [N][H][Wp][4] bf16, pixel w at column w + pad_l, zero elsewhere
+cudaError_t import_nchw_c4_padded(const float* src, void* dst, int N, int C, int H, int W, int Wp, int pad_l, cudaStream_t st);
+
 // ---- weight / BN preparation -------------------------------------------------------------------
 // OIHW fp32 -> [Cout_pad][Ktot] bf16 in the K order the conv kernel consumes.
 cudaError_t pack_conv_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cout_pad, int Cin, int R, int S,

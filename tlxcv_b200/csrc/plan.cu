@@ -25,14 +25,22 @@ struct TensorRt {
   size_t offset = 0;   // into the arena (internal tensors)
   int ext_index = -1;  // position among inputs / outputs (external tensors)
   int first_def = -1, last_use = -1;
+  int wp = 0, pad_l = 0;  // C<=4 stem inputs: rows stored with zero pad columns, pitch wp pixels (0 = dense)
+  bool elided = false;    // never materialised (the conv map between a stem and its fused max-pool)
 };
 
-enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax };
+enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
+                  kImplStem, kImplNop };
 
 struct OpRt {
   tlxcv_op_desc d;
   int impl = 0;
   TcConvLaunch tc;            // kImplTcConv
+  StemLaunch stem;            // kImplStem
+  StemGeometry geo;
+  bool use_stem = false;      // row-ring stem kernel chosen in the pre-pass
+  int pool_op = -1;           // index of the max-pool op fused into this stem (-1: none)
+  bool nop = false;           // fused into another op: no launch, no tensors of its own
   void* weights = nullptr;    // packed weights (owned)
   float* scale = nullptr;     // folded BN / bias (owned)
   float* shift = nullptr;
@@ -170,6 +178,53 @@ void set_info(OpRt& op, const char* kernel, int launches, int bound, double flop
   op.info.grid = grid, op.info.block = block, op.info.smem_bytes = smem, op.info.tile_n = tile_n;
 }
 
+// C_in <= 4 stem on the row-ring kernel (stem_rowring.cu); `out` is the pooled map when a max-pool is fused
+int compile_stem(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
+  tlxcv_ctx* ctx = p->ctx;
+  const tlxcv_op_desc& d = op.d;
+  const TensorRt& in = p->tensors[d.in0];
+  const TensorRt& out = p->tensors[d.out];
+  const StemGeometry& g = op.geo;
+  const int N = in.d.n, H = in.d.h, C = in.d.c, K = g.pairs ? g.block_n / 2 : g.block_n;
+  const bool pool = op.pool_op >= 0;
+  if (!d.filters) return fail(ctx, TLXCV_ERR_INVALID, "op conv: filters pointer is NULL");
+  if (pool ? (out.d.c != K || out.d.n != N) : (out.d.h != g.P || out.d.w != g.Q || out.d.c != K || out.d.n != N))
+    return fail(ctx, TLXCV_ERR_INVALID, "stem conv: output tensor shape mismatch");
+  if (out.d.role != TLXCV_ROLE_INTERNAL || out.d.dtype != TLXCV_ACT)
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "stem conv: output must be an internal activation tensor");
+  if (pool) {
+    const int Pp = (g.P + 2 - 3) / 2 + 1, Qp = (g.Q + 2 - 3) / 2 + 1;
+    if (out.d.h != Pp || out.d.w != Qp) return fail(ctx, TLXCV_ERR_INVALID, "stem conv + max-pool: pooled shape mismatch");
+  }
+  int rc;
+  if ((rc = dev_alloc(p, &op.scale, 256)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.shift, 256)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, fold_bn(op.scale, op.shift, d.bn_gamma, d.bn_beta, d.bn_mean, d.bn_var, d.bias, d.bn_eps, K, 256, st));
+  if (g.pairs) {  // GEMM column (parity, channel): the per-channel values twice
+    TLX_CUDA(ctx, cudaMemcpyAsync(op.scale + K, op.scale, K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    TLX_CUDA(ctx, cudaMemcpyAsync(op.shift + K, op.shift, K * sizeof(float), cudaMemcpyDeviceToDevice, st));
+  }
+  __nv_bfloat16* w = nullptr;
+  if ((rc = dev_alloc(p, &w, static_cast<size_t>(g.block_n) * d.r * 32)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, pack_stem_weights(d.filters, w, K, C, d.r, d.s, g, st));
+  op.weights = w;
+  std::string err = stem_rowring_prepare(op.stem, ctx->sm_count, g, reinterpret_cast<const __nv_bfloat16*>(p->arena + in.offset), N,
+                                         H, d.r, d.stride, d.pad, w, p->arena + out.offset, pool ? 1 : 0, pool ? out.d.h : 0,
+                                         pool ? out.d.w : 0);
+  if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
+  StemParams& sp = op.stem.p;
+  sp.scale = op.scale, sp.shift = op.shift, sp.act = d.act1, sp.alpha = d.alpha1;
+  op.impl = kImplStem;
+  const double M = static_cast<double>(N) * g.P * g.Q;
+  const double flops = 2.0 * M * K * C * d.r * d.s;
+  const double bytes = static_cast<double>(N) * H * in.d.w * 4 * 2 + static_cast<double>(K) * C * d.r * d.s * 2 +
+                       static_cast<double>(out.bytes);
+  char name[48];
+  snprintf(name, sizeof name, "stem_rowring_n%d%s%s", g.block_n, g.pairs ? "_pairs" : "", pool ? "_maxpool" : "");
+  set_info(op, name, 1, 0, flops, bytes, op.stem.grid, op.stem.threads, op.stem.smem, g.block_n);
+  return TLXCV_OK;
+}
+
 int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   tlxcv_ctx* ctx = p->ctx;
   const tlxcv_op_desc& d = op.d;
@@ -284,6 +339,7 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
 int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* outputs, cudaStream_t st) {
   tlxcv_ctx* ctx = p->ctx;
   const tlxcv_op_desc& d = op.d;
+  if (op.nop) return TLXCV_OK;
   const TensorRt& in = p->tensors[d.in0];
   const TensorRt& out = p->tensors[d.out];
   void* pin = tensor_ptr(p, d.in0, inputs, outputs);
@@ -292,8 +348,16 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
   if (!pin || !pout) return fail(ctx, TLXCV_ERR_INVALID, "NULL external tensor pointer");
   const int is_f32 = p->f32 ? 1 : 0;
   switch (op.impl) {
+    case kImplNop:
+      break;
     case kImplImport:
-      TLX_CUDA(ctx, import_nchw(static_cast<const float*>(pin), pout, in.d.n, in.d.c, in.d.h, in.d.w, out.cs, is_f32, st));
+      if (out.wp > 0)
+        TLX_CUDA(ctx, import_nchw_c4_padded(static_cast<const float*>(pin), pout, in.d.n, in.d.c, in.d.h, in.d.w, out.wp, out.pad_l, st));
+      else
+        TLX_CUDA(ctx, import_nchw(static_cast<const float*>(pin), pout, in.d.n, in.d.c, in.d.h, in.d.w, out.cs, is_f32, st));
+      break;
+    case kImplStem:
+      TLX_CUDA(ctx, stem_rowring_launch(op.stem, st));
       break;
     case kImplExport:
       TLX_CUDA(ctx, export_nchw(pin, static_cast<float*>(pout), in.d.n, in.d.c, in.d.h, in.d.w, is_f32, st));
@@ -374,6 +438,7 @@ int tlxcv_create(int device, tlxcv_ctx** out) {
                 device, prop.major, prop.minor);
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaSetDevice failed");
   cudaError_t e = tc_conv_set_attributes();
+  if (e == cudaSuccess) e = stem_rowring_set_attributes();
   if (e != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
   tlxcv_ctx* c = new tlxcv_ctx();
   c->device = device;
@@ -437,11 +502,52 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
   // ---- ops: validate indices, liveness ----
   p->ops.resize(n_ops);
   for (int i = 0; i < n_ops; ++i) {
-    OpRt& op = p->ops[i];
-    op.d = ops[i];
-    const tlxcv_op_desc& d = op.d;
+    p->ops[i].d = ops[i];
+    const tlxcv_op_desc& d = ops[i];
     if (d.in0 < 0 || d.in0 >= n_tensors || d.out < 0 || d.out >= n_tensors || d.in1 >= n_tensors)
       return fail(ctx, TLXCV_ERR_INVALID, "op %d: tensor index out of range", i);
+  }
+  // ---- pre-pass: C_in <= 4 stems go to the row-ring kernel (padded-column input written by the import
+  //      op), and a 3x3/s2/p1 max-pool that is the stem's only consumer is fused into its epilogue ----
+  if (!p->f32 && !getenv("TLXCV_NO_ROWRING")) {
+    for (int i = 0; i < n_ops; ++i) {
+      OpRt& op = p->ops[i];
+      const tlxcv_op_desc& d = op.d;
+      if (d.kind != TLXCV_OP_CONV || d.in1 >= 0 || d.act2 != TLXCV_ACT_NONE) continue;
+      TensorRt& in = p->tensors[d.in0];
+      if (in.d.c > 4 || in.d.role != TLXCV_ROLE_INTERNAL || in.d.dtype != TLXCV_ACT) continue;
+      if (p->tensors[d.out].d.role != TLXCV_ROLE_INTERNAL || p->tensors[d.out].d.dtype != TLXCV_ACT) continue;
+      int producer = -1, consumers = 0;
+      for (int k = 0; k < n_ops; ++k) {
+        if (p->ops[k].d.out == d.in0) producer = k;
+        if (p->ops[k].d.in0 == d.in0 || p->ops[k].d.in1 == d.in0) ++consumers;
+      }
+      if (producer < 0 || p->ops[producer].d.kind != TLXCV_OP_IMPORT_NCHW || consumers != 1) continue;
+      StemGeometry g;
+      if (!stem_rowring_geometry(g, in.d.c, p->tensors[d.out].d.c, in.d.h, in.d.w, d.r, d.s, d.stride, d.pad, d.dil, d.groups))
+        continue;
+      op.use_stem = true;
+      op.geo = g;
+      in.wp = g.Wp, in.pad_l = g.pad_l, in.cs = 4;
+      in.bytes = static_cast<size_t>(in.d.n) * in.d.h * g.Wp * 4 * 2;
+      if (g.pairs || g.Qw > 128 || getenv("TLXCV_NO_POOL_FUSION")) continue;
+      int pool = -1, users = 0;
+      for (int k = 0; k < n_ops; ++k)
+        if (p->ops[k].d.in0 == d.out || p->ops[k].d.in1 == d.out) ++users, pool = k;
+      if (users != 1 || pool < i) continue;
+      const tlxcv_op_desc& m = p->ops[pool].d;
+      if (m.kind != TLXCV_OP_MAXPOOL || m.r != 3 || m.s != 3 || m.stride != 2 || m.pad != 1) continue;
+      if (p->tensors[m.out].d.role != TLXCV_ROLE_INTERNAL) continue;
+      p->tensors[d.out].elided = true;
+      op.pool_op = pool;
+      op.d.out = m.out;
+      p->ops[pool].nop = true;
+    }
+  }
+  for (int i = 0; i < n_ops; ++i) {
+    OpRt& op = p->ops[i];
+    const tlxcv_op_desc& d = op.d;
+    if (op.nop) continue;
     for (int t : {d.in0, d.in1}) {
       if (t < 0) continue;
       if (p->tensors[t].d.role != TLXCV_ROLE_INPUT && p->tensors[t].first_def < 0)
@@ -458,6 +564,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     Arena arena;
     const bool no_reuse = getenv("TLXCV_NO_REUSE") != nullptr;  // debugging: keep every intermediate readable
     for (int i = 0; i < n_ops; ++i) {
+      if (p->ops[i].nop) continue;
       TensorRt& o = p->tensors[p->ops[i].d.out];
       if (o.d.role == TLXCV_ROLE_INTERNAL) o.offset = arena.alloc(o.bytes);
       for (int t : {p->ops[i].d.in0, p->ops[i].d.in1, p->ops[i].d.out}) {
@@ -483,12 +590,18 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     const TensorRt& o = p->tensors[d.out];
     const double in_bytes = static_cast<double>(in.bytes), out_bytes = static_cast<double>(o.bytes);
     int rc = TLXCV_OK;
+    if (op.nop) {
+      op.impl = kImplNop;
+      set_info(op, "(fused into the stem conv)", 0, 0, 0, 0, 0, 0, 0, 0);
+      continue;
+    }
     switch (d.kind) {
       case TLXCV_OP_IMPORT_NCHW:
         if (in.d.role != TLXCV_ROLE_INPUT || in.d.dtype != TLXCV_F32 || o.d.dtype != TLXCV_ACT || o.d.role != TLXCV_ROLE_INTERNAL)
           return fail(ctx, TLXCV_ERR_INVALID, "op %d: import expects external f32 -> internal activation", i);
         op.impl = kImplImport;
-        set_info(op, o.cs == 4 ? "import_nchw_c4" : "import_nchw_tile", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        set_info(op, o.wp > 0 ? "import_nchw_c4_padded" : (o.cs == 4 ? "import_nchw_c4" : "import_nchw_tile"), 1, 0, 0,
+                 in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_EXPORT_NCHW:
         if (o.d.role != TLXCV_ROLE_OUTPUT || o.d.dtype != TLXCV_F32 || in.d.dtype != TLXCV_ACT || in.cs != in.d.c)
@@ -498,7 +611,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         break;
       case TLXCV_OP_CONV:
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_ACT) return fail(ctx, TLXCV_ERR_INVALID, "op %d: conv tensors must be activations", i);
-        rc = compile_conv(p, op, st, false);
+        rc = op.use_stem ? compile_stem(p, op, st) : compile_conv(p, op, st, false);
         break;
       case TLXCV_OP_LINEAR:
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_F32 || in.d.h != 1 || in.d.w != 1)
@@ -661,6 +774,7 @@ int tlxcv_plan_read_tensor(tlxcv_plan* p, int t, void* dst, size_t dst_bytes, vo
   if (!p || t < 0 || t >= static_cast<int>(p->tensors.size()) || !dst) return TLXCV_ERR_INVALID;
   const TensorRt& T = p->tensors[t];
   if (T.d.role != TLXCV_ROLE_INTERNAL) return fail(p->ctx, TLXCV_ERR_INVALID, "read_tensor: tensor %d is external", t);
+  if (T.elided || T.wp > 0) return fail(p->ctx, TLXCV_ERR_UNSUPPORTED, "read_tensor: tensor %d is fused away or stored padded", t);
   if (dst_bytes < T.bytes) return fail(p->ctx, TLXCV_ERR_INVALID, "read_tensor: need %zu bytes", T.bytes);
   TLX_CUDA(p->ctx, cudaMemcpyAsync(dst, p->arena + T.offset, T.bytes, cudaMemcpyDeviceToDevice, static_cast<cudaStream_t>(stream)));
   return T.cs;
