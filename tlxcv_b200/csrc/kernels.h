@@ -78,10 +78,17 @@ struct StemParams {
   int R, sv, pad;
   int bands, band_rows, q_tiles;
   int pool, Pp, Qp;
+  // step = 2 output rows; ring of NG groups of G = 2*sv input-row slices; a step's window spans n_in
+  // slices = ng groups; stationary weight chain of nblk blocks, bblk[i] = first block of the stacked
+  // B operand of input-row position i
+  int G, n_in, ng, NG, slice_bytes, nblk;
+  int bblk[9];
   const float* scale;  // [block_n] (pair mode: the per-channel values twice)
   const float* shift;
   int act;
   float alpha;
+  const __nv_bfloat16* in;  // padded input [N][H][Wp][4] (L2 prefetch addresses; the operand loads go through tmapA)
+  int Wp;
   __nv_bfloat16* out;  // [N][P][Qw][block_n] == NHWC, or the pooled map [N][Pp][Qp][block_n]
   int ablate;          // debug: TLXCV_DEBUG_ABLATE_STEM bit mask (timing experiments; 0 in normal operation)
 };
@@ -100,8 +107,10 @@ std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry
                                  int Pp, int Qp);
 cudaError_t stem_rowring_launch(const StemLaunch& L, cudaStream_t st);
 cudaError_t stem_rowring_set_attributes();
-cudaError_t pack_stem_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cin, int R, int S, const StemGeometry& g,
-                              cudaStream_t st);
+// number of bf16 elements of the packed (chained) stem weights
+int stem_rowring_weight_elems(const StemGeometry& g, int R, int stride);
+cudaError_t pack_stem_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cin, int R, int S, int stride,
+                              const StemGeometry& g, cudaStream_t st);
 // NCHW fp32 (C <= 4) -> [N][H][Wp][4] bf16, pixel w at column w + pad_l, zero elsewhere
 cudaError_t import_nchw_c4_padded(const float* src, void* dst, int N, int C, int H, int W, int Wp, int pad_l, cudaStream_t st);
 

@@ -205,8 +205,8 @@ int compile_stem(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
     TLX_CUDA(ctx, cudaMemcpyAsync(op.shift + K, op.shift, K * sizeof(float), cudaMemcpyDeviceToDevice, st));
   }
   __nv_bfloat16* w = nullptr;
-  if ((rc = dev_alloc(p, &w, static_cast<size_t>(g.block_n) * d.r * 32)) != TLXCV_OK) return rc;
-  TLX_CUDA(ctx, pack_stem_weights(d.filters, w, K, C, d.r, d.s, g, st));
+  if ((rc = dev_alloc(p, &w, static_cast<size_t>(stem_rowring_weight_elems(g, d.r, d.stride)))) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, pack_stem_weights(d.filters, w, K, C, d.r, d.s, d.stride, g, st));
   op.weights = w;
   std::string err = stem_rowring_prepare(op.stem, ctx->sm_count, g, reinterpret_cast<const __nv_bfloat16*>(p->arena + in.offset), N,
                                          H, d.r, d.stride, d.pad, w, p->arena + out.offset, pool ? 1 : 0, pool ? out.d.h : 0,
