@@ -117,7 +117,13 @@ LAYERS = {
     "gemm_m_tail_49px": (dict(n=1, cin=64, hw=7, cout=256, k=1, stride=1, pad=0, act="relu"), "conv_tcgen05_tiled"),
     "gemm_c_tails_24_144": (dict(n=2, cin=24, hw=12, cout=144, k=1, stride=1, pad=0, act="relu6"), "conv_tcgen05_tiled"),
     "gemm_cout_24": (dict(n=2, cin=96, hw=12, cout=24, k=1, stride=1, pad=0), "conv_tcgen05_tiled"),
-    "im2col_3x3": (dict(n=2, cin=64, hw=14, cout=64, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col"),
+    "im2col_3x3": (dict(n=2, cin=64, hw=7, cout=64, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col"),
+    "slab_3x3_c64_w14": (dict(n=2, cin=64, hw=14, cout=64, k=3, stride=1, pad=1, act="relu"), "conv3x3_slab"),
+    "slab_3x3_c64_w56": (dict(n=3, cin=64, hw=56, cout=64, k=3, stride=1, pad=1, act="relu"), "conv3x3_slab"),
+    "slab_3x3_c64_w28_leaky": (dict(n=2, cin=64, hw=28, cout=64, k=3, stride=1, pad=1, act="leaky"), "conv3x3_slab"),
+    "slab_3x3_c64_w21_odd": (dict(n=5, cin=64, hw=21, cout=64, k=3, stride=1, pad=1), "conv3x3_slab"),
+    "slab_3x3_c64_w62_max": (dict(n=1, cin=64, hw=62, cout=64, k=3, stride=1, pad=1, act="relu6"), "conv3x3_slab"),
+    "slab_3x3_c64_many_bands": (dict(n=160, cin=64, hw=10, cout=64, k=3, stride=1, pad=1, act="relu"), "conv3x3_slab"),
     "im2col_3x3_s2": (dict(n=2, cin=128, hw=28, cout=128, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_im2col"),
     "im2col_3x3_7x7_images_wrap": (dict(n=5, cin=256, hw=7, cout=256, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col"),
     "im2col_1x1_s2_downsample": (dict(n=2, cin=256, hw=14, cout=512, k=1, stride=2, pad=0), "conv_tcgen05_im2col"),

@@ -23,6 +23,21 @@ __device__ __forceinline__ float apply_act(float v, int act, float alpha) {
   }
 }
 
+// activation over a register tile; the switch is outside the element loop
+template <int N>
+__device__ __forceinline__ void act_regs(float (&f)[N], int act, float alpha) {
+  if (act == TLXCV_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fmaxf(f[j], 0.0f);
+  } else if (act == TLXCV_ACT_RELU6) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = fminf(fmaxf(f[j], 0.0f), 6.0f);
+  } else if (act == TLXCV_ACT_LEAKY) {
+#pragma unroll
+    for (int j = 0; j < N; ++j) f[j] = f[j] > 0.0f ? f[j] : f[j] * alpha;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // 8-element activation vectors: bf16 -> one 16 B access, fp32 -> two
 // ------------------------------------------------------------------------------------------------

@@ -114,6 +114,35 @@ cudaError_t pack_stem_weights(const float* oihw, __nv_bfloat16* dst, int Cout, i
 // NCHW fp32 (C <= 4) -> [N][H][Wp][4] bf16, pixel w at column w + pad_l, zero elsewhere
 cudaError_t import_nchw_c4_padded(const float* src, void* dst, int N, int C, int H, int W, int Wp, int pad_l, cudaStream_t st);
 
+// ---- 3x3 stride-1 conv with 64 input channels as a slab implicit GEMM (conv3x3_slab.cu) -----------
+struct SlabParams {
+  int N, H, W;
+  int T;                 // output rows per step = floor(128 / (W + 2))
+  int NG;                // ring depth in groups of T input rows
+  int bands, band_rows;  // bands per image; output rows per band
+  const __nv_bfloat16* in;  // NHWC input (L2 prefetch addresses; operand loads go through tmapA)
+  __nv_bfloat16* out;       // NHWC output
+  const float* scale;
+  const float* shift;
+  int act;
+  float alpha;
+  int ablate;  // debug: TLXCV_DEBUG_ABLATE_SLAB bit mask (timing experiments; 0 in normal operation)
+  unsigned long long* trace;  // debug: TLXCV_DEBUG_TRACE_SLAB timeline buffer (NULL in normal operation)
+};
+
+struct SlabLaunch {
+  CUtensorMap tmapA, tmapB;
+  SlabParams p;
+  int block_n, grid, threads, smem;
+};
+
+bool conv3x3_slab_supported(int Cin, int Cout, int H, int W, int R, int S, int stride, int pad, int dil, int groups,
+                            bool residual);
+std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat16* in, int N, int H, int W, int Cout,
+                                 const __nv_bfloat16* packed_w, int Ktot, void* out);
+cudaError_t conv3x3_slab_launch(const SlabLaunch& L, cudaStream_t st);
+cudaError_t conv3x3_slab_set_attributes();
+
 // ---- weight / BN preparation -------------------------------------------------------------------
 // OIHW fp32 -> [Cout_pad][Ktot] bf16 in the K order the conv kernel consumes.
 cudaError_t pack_conv_weights(const float* oihw, __nv_bfloat16* dst, int Cout, int Cout_pad, int Cin, int R, int S,

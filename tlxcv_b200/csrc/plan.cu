@@ -30,13 +30,14 @@ struct TensorRt {
 };
 
 enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
-                  kImplStem, kImplNop };
+                  kImplStem, kImplSlab, kImplNop };
 
 struct OpRt {
   tlxcv_op_desc d;
   int impl = 0;
   TcConvLaunch tc;            // kImplTcConv
   StemLaunch stem;            // kImplStem
+  SlabLaunch slab;            // kImplSlab
   StemGeometry geo;
   bool use_stem = false;      // row-ring stem kernel chosen in the pre-pass
   int pool_op = -1;           // index of the max-pool op fused into this stem (-1: none)
@@ -317,6 +318,19 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   }
   if (d.act2 != TLXCV_ACT_NONE && d.act2 != TLXCV_ACT_RELU)
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: only ReLU (or nothing) may follow the residual add on the tensor-core path");
+  if (!is_linear && out_bf16 && in.cs == C &&
+      conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups, d.in1 >= 0 || d.act2 != TLXCV_ACT_NONE)) {
+    // wide 3x3 stride-1 layer: slab kernel (each input row fetched once, stationary weights)
+    std::string serr = conv3x3_slab_prepare(op.slab, ctx->sm_count, act_in, N, H, W, K, w, Ktot, out_bf16);
+    if (serr.empty()) {
+      SlabParams& sp = op.slab.p;
+      sp.scale = op.scale, sp.shift = op.shift, sp.act = d.act1, sp.alpha = d.alpha1;
+      op.impl = kImplSlab;
+      set_info(op, "conv3x3_slab_n64", 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.slab.grid, op.slab.threads,
+               op.slab.smem, op.slab.block_n);
+      return TLXCV_OK;
+    }
+  }
   if (d.act2 != TLXCV_ACT_NONE && d.in1 < 0)
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: a second activation without a residual add");
   std::string err = tc_conv_prepare(op.tc, ctx->sm_count, act_in, N, H, W, C, in.cs, w, Ktot, K, R, S, stride, pad, dil,
@@ -358,6 +372,9 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
       break;
     case kImplStem:
       TLX_CUDA(ctx, stem_rowring_launch(op.stem, st));
+      break;
+    case kImplSlab:
+      TLX_CUDA(ctx, conv3x3_slab_launch(op.slab, st));
       break;
     case kImplExport:
       TLX_CUDA(ctx, export_nchw(pin, static_cast<float*>(pout), in.d.n, in.d.c, in.d.h, in.d.w, is_f32, st));
@@ -439,6 +456,7 @@ int tlxcv_create(int device, tlxcv_ctx** out) {
   if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaSetDevice failed");
   cudaError_t e = tc_conv_set_attributes();
   if (e == cudaSuccess) e = stem_rowring_set_attributes();
+  if (e == cudaSuccess) e = conv3x3_slab_set_attributes();
   if (e != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
   tlxcv_ctx* c = new tlxcv_ctx();
   c->device = device;

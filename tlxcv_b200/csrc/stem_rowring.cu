@@ -128,20 +128,6 @@ __device__ __forceinline__ Item decode_item(const StemParams& p, int item) {
   return it;
 }
 
-template <int N>
-__device__ __forceinline__ void act_regs(float (&f)[N], int act, float alpha) {
-  if (act == TLXCV_ACT_RELU) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) f[j] = fmaxf(f[j], 0.0f);
-  } else if (act == TLXCV_ACT_RELU6) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) f[j] = fminf(fmaxf(f[j], 0.0f), 6.0f);
-  } else if (act == TLXCV_ACT_LEAKY) {
-#pragma unroll
-    for (int j = 0; j < N; ++j) f[j] = f[j] > 0.0f ? f[j] : f[j] * alpha;
-  }
-}
-
 // first chain block of the stacked operand [B_i ; B_{i-SV}] for input-row position i of a step (see build_chain)
 template <int R, int SV>
 __host__ __device__ constexpr int chain_block(int i) {
