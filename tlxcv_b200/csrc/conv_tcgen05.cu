@@ -22,6 +22,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "common.cuh"
 #include "kernels.h"
@@ -61,6 +62,16 @@ struct Cfg {
   }
 };
 
+// debug timeline (TLXCV_DEBUG_TRACE_CONV=<file>): CTA 0 records %clock64 at pipeline events, role-major
+constexpr int kTraceLenC = 4096;
+__device__ __forceinline__ void trace_c(unsigned long long* buf, int role, int& idx) {
+  if (buf != nullptr && blockIdx.x == 0 && idx < kTraceLenC) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
+    buf[role * kTraceLenC + idx++] = t;
+  }
+}
+
 struct PipeState {
   uint32_t stage = 0, phase = 0;
   __device__ __forceinline__ void advance(uint32_t n_stages) {
@@ -99,6 +110,7 @@ struct EpiArgs {
   int M, Cout, n_tiles, num_tiles, first_tile, tile_stride;
   float alpha1, alpha2;
   int ablate;
+  unsigned long long* trace;
 };
 
 template <int ACT>
@@ -155,12 +167,16 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
 
   uint32_t it = 0;  // items processed
   uint32_t acc = 0, acc_phase = 0;
+  int tr = 0;
+  const bool tracer = a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;  // warp 2
   for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
     const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = min(kCpw, max(0, (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
+    if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
+    if (tracer) trace_c(a.trace, 2, tr);  // [3k+1] accumulator complete
     if (n_my == 0 && lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);  // nothing to read: release at once
 #pragma unroll 1
     for (int ci = 0; ci < n_my; ++ci, ++it) {
@@ -261,6 +277,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       acc = 0;
       acc_phase ^= 1;
     }
+    if (tracer) trace_c(a.trace, 2, tr);  // [3k+2] all chunks of the tile processed
   }
   if (!F32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -325,7 +342,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     if (lane == 0) {
       PipeState ps;
       const int PQ = p.P * p.Q;
+      int tr = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        trace_c(p.trace, 0, tr);  // [2k] tile start
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         const int m0 = m_tile * kBlockM, n0 = n_tile * BLOCK_N;
         int img = 0, base_h = 0, base_w = 0;
@@ -357,6 +376,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           tma_load_2d(a_dst + kABytes, &tmapB, bar, kb * kBlockK, n0);
           ps.advance(n_stages);
         }
+        trace_c(p.trace, 0, tr);  // [2k+1] all loads of the tile issued
       }
     }
   } else if (warp == 1) {
@@ -365,13 +385,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
       PipeState ps;
       uint32_t acc = 0, acc_phase = 0;
+      int tr = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        trace_c(p.trace, 1, tr);  // [4k] tile start
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
+        trace_c(p.trace, 1, tr);  // [4k+1] accumulator free
         const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&full_bar[ps.stage]), ps.phase);
           tcgen05_fence_after();
+          if (kb == 0) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
           const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
           const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
           const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kABytes);
@@ -384,6 +408,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           ps.advance(n_stages);
         }
         umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator ready for the epilogue
+        trace_c(p.trace, 1, tr);  // [4k+3] all MMAs of the tile issued
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
@@ -407,6 +432,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.first_tile = blockIdx.x, a.tile_stride = gridDim.x;
     a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
     a.ablate = p.ablate;
+    a.trace = p.trace;
     const int lg = warp & 3, cgroup = (warp - 2) >> 2;
     const bool res = kRes && p.residual != nullptr;
 #define TLXCV_EPI(A1)                                                                                          \
@@ -571,6 +597,23 @@ std::string encode_im2col(CUtensorMap* map, const void* base, int N, int H, int 
 
 template <int BLOCK_N, int MODE>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
+  static const char* trace_path = getenv("TLXCV_DEBUG_TRACE_CONV");  // debugging: dump CTA 0's timeline of the LAST conv launch
+  if (trace_path != nullptr) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 3 * kTraceLenC * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 3 * kTraceLenC * sizeof(unsigned long long), st);
+    ConvKernelParams p = L.p;
+    p.trace = dbuf;
+    conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, p);
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> h(3 * kTraceLenC);
+    cudaMemcpy(h.data(), dbuf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+      fclose(f);
+    }
+    return cudaGetLastError();
+  }
   conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.p);
   return cudaGetLastError();
 }
