@@ -38,7 +38,7 @@ constexpr int kEpiWarps = 8;                    // warps 2..9
 constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
 constexpr int kMaxRing = 4;                     // per epilogue warp: ring of 2 or 4 (32 rows x 64 B) SWIZZLE_64B buffers
 constexpr int kSmemLimit = 232448;              // 227 KB of dynamic shared memory per CTA
-constexpr int kScaleCacheBytes = 2 * 256 * 4;   // [scale | shift] of one N tile (used when the layer has one N tile)
+constexpr int kScaleBufBytes = 2 * 256 * 4;      // [scale | shift] of one N tile; the kernel has sc_bufs (1 or 2) of them
 constexpr int kBarrierBytes = 512;              // pipeline barriers + kEpiWarps * kRing residual barriers
 constexpr int kMaxStages = 8;
 constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
@@ -53,12 +53,12 @@ struct Cfg {
   // and therefore the stage count are chosen per layer (deep ring for residual / HBM-bound layers,
   // more operand stages for MMA-bound ones)
   static constexpr int staging_bytes(int ring) { return kEpiWarps * ring * 2048; }
-  static constexpr int stages_for(int ring) {
-    const int n = (kSmemLimit - staging_bytes(ring) - kScaleCacheBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int stages_for(int ring, int sc_bufs) {
+    const int n = (kSmemLimit - staging_bytes(ring) - sc_bufs * kScaleBufBytes - kBarrierBytes) / kStageBytes;
     return n > kMaxStages ? kMaxStages : n;
   }
-  static constexpr int smem_bytes(int ring) {
-    return stages_for(ring) * kStageBytes + staging_bytes(ring) + kScaleCacheBytes + kBarrierBytes;
+  static constexpr int smem_bytes(int ring, int sc_bufs) {
+    return stages_for(ring, sc_bufs) * kStageBytes + staging_bytes(ring) + sc_bufs * kScaleBufBytes + kBarrierBytes;
   }
 };
 
@@ -101,7 +101,9 @@ __device__ __forceinline__ void act_inplace(float (&f)[N], int act, float alpha)
 // memory; re-reading them through the uniform datapath inside the item loop costs latency).
 struct EpiArgs {
   uint32_t tmem_base, tmem_full_bar, tmem_empty_bar, ring, res_bar;  // smem addresses are shared-space offsets
-  const float* sc_cache;  // smem [scale(256) | shift(256)] when the layer has a single N tile, else nullptr
+  const float* sc_cache;  // smem 2 x [scale(256) | shift(256)]: filled once when the layer has a single N tile (sc_static),
+                          // else buffer [acc] is refreshed by the epilogue warps for every tile
+  int sc_mode;  // 0: smem buffer filled once; 1: smem buffer [acc] refreshed per tile; 2: global loads per chunk
   const float* scale;
   const float* shift;
   float* out_f32;
@@ -174,9 +176,26 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = min(kCpw, max(0, (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
+    float4 sc_pf = make_float4(0.f, 0.f, 0.f, 0.f), sh_pf = sc_pf;
+    if (a.sc_mode == 1 && lane < kCpw * 8) {
+      // this warp's slice of the tile's scale / shift: fetched now, the latency hides behind the accumulator wait
+      sc_pf = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + c_first * 32) + lane);
+      sh_pf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + c_first * 32) + lane);
+    }
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
     if (tracer) trace_c(a.trace, 2, tr);  // [3k+1] accumulator complete
+    float* sc_buf = const_cast<float*>(a.sc_cache) + (a.sc_mode == 1 ? acc * 512 : 0);
+    if (a.sc_mode == 1) {
+      // Safe to overwrite buffer [acc] now: its previous user (the tile two back) was fully read before every
+      // warp released that accumulator (the arrive below comes after the last scale/shift read), and this
+      // tile's MMAs could only start after that.  The four warps of a column group write identical values.
+      if (lane < kCpw * 8) {
+        reinterpret_cast<float4*>(sc_buf + c_first * 32)[lane] = sc_pf;
+        reinterpret_cast<float4*>(sc_buf + 256 + c_first * 32)[lane] = sh_pf;
+      }
+      __syncwarp();
+    }
     if (n_my == 0 && lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);  // nothing to read: release at once
 #pragma unroll 1
     for (int ci = 0; ci < n_my; ++ci, ++it) {
@@ -198,17 +217,10 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         __syncwarp();
       }
       tmem_ld_wait();
-      if (ci == n_my - 1) {
-        // this warp's last read of the accumulator: hand the TMEM buffer back to the MMA warp early
-        // (one arrival per warp: 256 same-address smem atomics per tile were a measurable cost)
-        tcgen05_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);
-      }
       float f[32];
-      if (a.sc_cache != nullptr) {
-        const float4* scp = reinterpret_cast<const float4*>(a.sc_cache + chunk * 32);
-        const float4* shp = reinterpret_cast<const float4*>(a.sc_cache + 256 + chunk * 32);
+      if (a.sc_mode != 2) {
+        const float4* scp = reinterpret_cast<const float4*>(sc_buf + chunk * 32);
+        const float4* shp = reinterpret_cast<const float4*>(sc_buf + 256 + chunk * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const float4 sc = scp[j], sh = shp[j];
@@ -227,6 +239,14 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
           f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), a.alpha1);
           f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), a.alpha1);
         }
+      }
+      if (ci == n_my - 1) {
+        // this warp's last read of the accumulator and of the tile's scale/shift buffer: hand the TMEM
+        // buffer back to the MMA warp (one arrival per warp: 256 same-address smem atomics per tile were a
+        // measurable cost)
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);
       }
       if (F32) {
         const int gr = m0 + lane;
@@ -296,7 +316,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   const int staging_bytes = kEpiWarps * ring * 2048;
   uint8_t* staging = smem + n_stages * C::kStageBytes;
   float* sc_cache = reinterpret_cast<float*>(staging + staging_bytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + kScaleCacheBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + p.sc_bufs * kScaleBufBytes);
   uint64_t* full_bar = bars;                       // [kStages]  operands landed
   uint64_t* empty_bar = bars + kMaxStages;         // [kStages]  MMAs that read the stage retired
   uint64_t* tmem_full_bar = bars + 2 * kMaxStages; // [2]        accumulator complete
@@ -424,7 +444,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.tmem_empty_bar = smem_u32(tmem_empty_bar);
     a.ring = smem_u32(staging + (warp - 2) * (ring * 2048));
     a.res_bar = smem_u32(res_bar + (warp - 2) * kMaxRing);
-    a.sc_cache = sc_cached ? sc_cache : nullptr;
+    a.sc_cache = sc_cache;
+    a.sc_mode = sc_cached ? 0 : (p.sc_bufs == 2 ? 1 : 2);
     a.scale = p.scale, a.shift = p.shift;
     a.out_f32 = reinterpret_cast<float*>(p.out);
     a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
@@ -621,14 +642,17 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
 template <int BLOCK_N, int MODE>
 cudaError_t set_attr_t() {
   return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              std::max(Cfg<BLOCK_N>::smem_bytes(2), Cfg<BLOCK_N>::smem_bytes(4)));
+                              std::max(std::max(Cfg<BLOCK_N>::smem_bytes(2, 1), Cfg<BLOCK_N>::smem_bytes(4, 1)),
+                                       std::max(Cfg<BLOCK_N>::smem_bytes(2, 2), Cfg<BLOCK_N>::smem_bytes(4, 2))));
 }
 
-int smem_for(int block_n, int ring) {
-  return block_n == 256 ? Cfg<256>::smem_bytes(ring) : (block_n == 128 ? Cfg<128>::smem_bytes(ring) : Cfg<64>::smem_bytes(ring));
+int smem_for(int block_n, int ring, int sc_bufs) {
+  return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs)
+                        : (block_n == 128 ? Cfg<128>::smem_bytes(ring, sc_bufs) : Cfg<64>::smem_bytes(ring, sc_bufs));
 }
-int stages_for(int block_n, int ring) {
-  return block_n == 256 ? Cfg<256>::stages_for(ring) : (block_n == 128 ? Cfg<128>::stages_for(ring) : Cfg<64>::stages_for(ring));
+int stages_for(int block_n, int ring, int sc_bufs) {
+  return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs)
+                        : (block_n == 128 ? Cfg<128>::stages_for(ring, sc_bufs) : Cfg<64>::stages_for(ring, sc_bufs));
 }
 
 }  // namespace
@@ -729,8 +753,12 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only: results are wrong
   p.ring = (residual_bf16 != nullptr || p.num_kb <= 8) ? 4 : 2;
   if (!out_bf16) p.ring = 2;
-  p.stages = stages_for(block_n, p.ring);
-  L.smem = smem_for(block_n, p.ring);
+  // scale/shift: one smem buffer filled once (single N tile); two buffers refreshed per tile by the epilogue
+  // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
+  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2) == stages_for(block_n, p.ring, 1)) ? 2 : 1;
+  if (const char* e = getenv("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
+  p.stages = stages_for(block_n, p.ring, p.sc_bufs);
+  L.smem = smem_for(block_n, p.ring, p.sc_bufs);
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   L.grid = static_cast<int>(std::min<long long>(tiles, sm_count));
 

@@ -44,6 +44,7 @@ struct ConvKernelParams {
   // shared-memory configuration chosen per layer
   int ablate;  // debug: TLXCV_DEBUG_ABLATE bit mask (timing experiments; 0 in normal operation)
   int stages, ring;  // operand pipeline stages; epilogue store/residual ring depth per warp (2 or 4)
+  int sc_bufs;       // scale/shift smem buffers: 1 (filled once, or unused) or 2 (refreshed per tile)
   unsigned long long* trace;  // debug: TLXCV_DEBUG_TRACE_CONV timeline buffer (NULL in normal operation)
 };
 
