@@ -161,6 +161,8 @@ conv3x3_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t NG = static_cast<uint32_t>(p.NG);
+  pdl_wait();               // the previous kernel's activations are complete and visible from here on
+  pdl_launch_dependents();  // the next kernel may take this SM as soon as this CTA exits
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then T input rows per step =====================
@@ -469,8 +471,7 @@ cudaError_t conv3x3_slab_launch(const SlabLaunch& L, cudaStream_t st) {
     }
     return cudaGetLastError();
   }
-  conv3x3_slab_kernel<64><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.p);
-  return cudaGetLastError();
+  return launch_pdl(conv3x3_slab_kernel<64>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.p);
 }
 
 }  // namespace tlxcv

@@ -356,6 +356,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();               // the previous kernel's activations are complete and visible from here on
+  pdl_launch_dependents();  // the next kernel may take this SM as soon as this CTA exits
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -635,8 +637,7 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
     }
     return cudaGetLastError();
   }
-  conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.p);
-  return cudaGetLastError();
+  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.p);
 }
 
 template <int BLOCK_N, int MODE>

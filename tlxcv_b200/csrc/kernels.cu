@@ -17,6 +17,14 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// forward kernels are launched with the programmatic-dependent-launch attribute (common.cuh); the macro keeps
+// template commas inside the kernel name out of the argument list
+#define TLXCV_LAUNCH(kernel, grid, block, smem, st, ...)                                              \
+  do {                                                                                              \
+    cudaError_t _le = launch_pdl((kernel), dim3(grid), dim3(block), (smem), (st), __VA_ARGS__);     \
+    if (_le != cudaSuccess) return _le;                                                             \
+  } while (0)
+
 inline int blocks_for(size_t work, int threads = kThreads) {
   size_t b = (work + threads - 1) / threads;
   return static_cast<int>(b < 1 ? 1 : (b > 0x7fffffffull ? 0x7fffffffull : b));
@@ -114,6 +122,7 @@ __global__ void fold_bn_kernel(float* scale, float* shift, const float* gamma, c
 template <typename T>
 __global__ void import_nchw_smallc_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, size_t HW,
                                           size_t total) {
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const size_t n = idx / HW, hw = idx % HW;
@@ -131,6 +140,7 @@ __global__ void import_nchw_smallc_kernel(const float* __restrict__ src, T* __re
 // general transpose [N][C][HW] fp32 -> [N][HW][C] T through a 32x32 smem tile
 template <typename T>
 __global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const float* s = src + static_cast<size_t>(n) * C * HW;
@@ -148,6 +158,7 @@ __global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __rest
 
 template <typename T>
 __global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+  pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
   const T* s = src + static_cast<size_t>(n) * HW * C;
@@ -169,6 +180,7 @@ __global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __rest
 template <typename T, int KS>  // KS = compile-time window (3) or 0 for a runtime window
 __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C8, int P, int Q,
                                     int k_rt, int stride, int pad, size_t total) {
+  pdl_wait();
   const int k = KS > 0 ? KS : k_rt;
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
@@ -202,6 +214,7 @@ __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
 // global average pool: block per image, thread per 8-channel group, fp32 accumulation in pixel order
 template <typename T>
 __global__ void gap_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int HW, int C8) {
+  pdl_wait();
   const int n = blockIdx.x;
   const T* s = src + static_cast<size_t>(n) * HW * C8 * 8;
   const float inv = 1.0f / static_cast<float>(HW);
@@ -227,6 +240,7 @@ __global__ void dwconv_nhwc_kernel(const T* __restrict__ src, const T* __restric
                                    const float* __restrict__ scale, const float* __restrict__ shift,
                                    const T* __restrict__ residual, int H, int W, int C8, int P, int Q, int R, int S,
                                    int stride, int pad, int act1, float alpha1, int act2, float alpha2, size_t total) {
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int c8 = static_cast<int>(idx % C8);
@@ -291,6 +305,7 @@ dwconv3x3_nhwc_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16
                       const float* __restrict__ shift, const __nv_bfloat16* __restrict__ residual, int H, int W,
                       int C4, int P, int Q, int PT, int QT, int act1, float alpha1, int act2, float alpha2,
                       size_t total) {
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int c4 = static_cast<int>(idx % C4);
@@ -395,6 +410,7 @@ dwconv3x3_nhwc_kernel(const __nv_bfloat16* __restrict__ src, const __nv_bfloat16
 template <typename T>
 __global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ dst, size_t n8, int act,
                                float alpha) {
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= n8) return;
   float x[8], y[8];
@@ -411,6 +427,7 @@ __global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b,
 
 // one warp per row; first maximal index wins (torch.argmax on ties returns the first occurrence)
 __global__ void argmax_rows_kernel(const float* __restrict__ logits, long long* __restrict__ dst, int N, int K) {
+  pdl_wait();
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
   if (row >= N) return;
@@ -511,17 +528,17 @@ cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W,
   if (C <= 4 && Cs == 4) {
     const size_t total = static_cast<size_t>(N) * HW;
     if (is_f32)
-      import_nchw_smallc_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(src, static_cast<float*>(dst), C, HW, total);
+      TLXCV_LAUNCH(import_nchw_smallc_kernel<float>, blocks_for(total), kThreads, 0, st, src, static_cast<float*>(dst), C, HW, total);
     else
-      import_nchw_smallc_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), C, HW, total);
+      TLXCV_LAUNCH(import_nchw_smallc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, src, static_cast<__nv_bfloat16*>(dst), C, HW, total);
     return cudaGetLastError();
   }
   if (Cs != C) return cudaErrorInvalidValue;
   dim3 grid(static_cast<unsigned>((HW + 31) / 32), (C + 31) / 32, N), block(32, 8);
   if (is_f32)
-    import_nchw_tile_kernel<float><<<grid, block, 0, st>>>(src, static_cast<float*>(dst), C, static_cast<int>(HW));
+    TLXCV_LAUNCH(import_nchw_tile_kernel<float>, grid, block, 0, st, src, static_cast<float*>(dst), C, static_cast<int>(HW));
   else
-    import_nchw_tile_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(src, static_cast<__nv_bfloat16*>(dst), C, static_cast<int>(HW));
+    TLXCV_LAUNCH(import_nchw_tile_kernel<__nv_bfloat16>, grid, block, 0, st, src, static_cast<__nv_bfloat16*>(dst), C, static_cast<int>(HW));
   return cudaGetLastError();
 }
 
@@ -529,9 +546,9 @@ cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W,
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
   if (is_f32)
-    export_nchw_tile_kernel<float><<<grid, block, 0, st>>>(static_cast<const float*>(src), dst, C, HW);
+    TLXCV_LAUNCH(export_nchw_tile_kernel<float>, grid, block, 0, st, static_cast<const float*>(src), dst, C, HW);
   else
-    export_nchw_tile_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(static_cast<const __nv_bfloat16*>(src), dst, C, HW);
+    TLXCV_LAUNCH(export_nchw_tile_kernel<__nv_bfloat16>, grid, block, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
   return cudaGetLastError();
 }
 
@@ -540,11 +557,11 @@ cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C,
   if (C % 8) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
   if (is_f32)
-    maxpool_nhwc_kernel<float, 0><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+    TLXCV_LAUNCH((maxpool_nhwc_kernel<float, 0>), blocks_for(total), kThreads, 0, st, static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   else if (k == 3)
-    maxpool_nhwc_kernel<__nv_bfloat16, 3><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+    TLXCV_LAUNCH((maxpool_nhwc_kernel<__nv_bfloat16, 3>), blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   else
-    maxpool_nhwc_kernel<__nv_bfloat16, 0><<<blocks_for(total), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+    TLXCV_LAUNCH((maxpool_nhwc_kernel<__nv_bfloat16, 0>), blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   return cudaGetLastError();
 }
 
@@ -552,9 +569,9 @@ cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f3
   if (C % 8) return cudaErrorInvalidValue;
   const int threads = C / 8 >= 256 ? 256 : (C / 8 >= 128 ? 128 : 64);
   if (is_f32)
-    gap_nhwc_kernel<float><<<N, threads, 0, st>>>(static_cast<const float*>(src), static_cast<float*>(dst), HW, C / 8);
+    TLXCV_LAUNCH(gap_nhwc_kernel<float>, N, threads, 0, st, static_cast<const float*>(src), static_cast<float*>(dst), HW, C / 8);
   else
-    gap_nhwc_kernel<__nv_bfloat16><<<N, threads, 0, st>>>(static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), HW, C / 8);
+    TLXCV_LAUNCH(gap_nhwc_kernel<__nv_bfloat16>, N, threads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), HW, C / 8);
   return cudaGetLastError();
 }
 
@@ -571,24 +588,24 @@ cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const flo
       constexpr int TH = 4, TW = 2;
       const int PT = (P + TH - 1) / TH, QT = (Q + TW - 1) / TW;
       const size_t total = static_cast<size_t>(N) * PT * QT * (C / 4);
-      dwconv3x3_nhwc_kernel<1, TH, TW><<<blocks_for(total, 128), 128, 0, st>>>(
+      TLXCV_LAUNCH((dwconv3x3_nhwc_kernel<1, TH, TW>), blocks_for(total, 128), 128, 0, st, 
           x, wp, y, scale, shift, rp, H, W, C / 4, P, Q, PT, QT, act1, alpha1, act2, alpha2, total);
     } else {
       constexpr int TH = 2, TW = 2;
       const int PT = (P + TH - 1) / TH, QT = (Q + TW - 1) / TW;
       const size_t total = static_cast<size_t>(N) * PT * QT * (C / 4);
-      dwconv3x3_nhwc_kernel<2, TH, TW><<<blocks_for(total, 128), 128, 0, st>>>(
+      TLXCV_LAUNCH((dwconv3x3_nhwc_kernel<2, TH, TW>), blocks_for(total, 128), 128, 0, st, 
           x, wp, y, scale, shift, rp, H, W, C / 4, P, Q, PT, QT, act1, alpha1, act2, alpha2, total);
     }
     return cudaGetLastError();
   }
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
   if (is_f32)
-    dwconv_nhwc_kernel<float><<<blocks_for(total), kThreads, 0, st>>>(
+    TLXCV_LAUNCH(dwconv_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, 
         static_cast<const float*>(src), static_cast<const float*>(w_rsc), static_cast<float*>(dst), scale, shift,
         static_cast<const float*>(residual), H, W, C / 8, P, Q, R, S, stride, pad, act1, alpha1, act2, alpha2, total);
   else
-    dwconv_nhwc_kernel<__nv_bfloat16><<<blocks_for(total), kThreads, 0, st>>>(
+    TLXCV_LAUNCH(dwconv_nhwc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, 
         static_cast<const __nv_bfloat16*>(src), static_cast<const __nv_bfloat16*>(w_rsc),
         static_cast<__nv_bfloat16*>(dst), scale, shift, static_cast<const __nv_bfloat16*>(residual), H, W, C / 8, P, Q,
         R, S, stride, pad, act1, alpha1, act2, alpha2, total);
@@ -599,15 +616,15 @@ cudaError_t add_act(const void* a, const void* b, void* dst, size_t n, int act, 
   if (n % 8) return cudaErrorInvalidValue;
   const size_t n8 = n / 8;
   if (is_f32)
-    add_act_kernel<float><<<blocks_for(n8), kThreads, 0, st>>>(static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(dst), n8, act, alpha);
+    TLXCV_LAUNCH(add_act_kernel<float>, blocks_for(n8), kThreads, 0, st, static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(dst), n8, act, alpha);
   else
-    add_act_kernel<__nv_bfloat16><<<blocks_for(n8), kThreads, 0, st>>>(static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(dst), n8, act, alpha);
+    TLXCV_LAUNCH(add_act_kernel<__nv_bfloat16>, blocks_for(n8), kThreads, 0, st, static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(dst), n8, act, alpha);
   return cudaGetLastError();
 }
 
 cudaError_t argmax_rows(const float* logits, long long* dst, int N, int K, cudaStream_t st) {
   const int warps_per_block = 8;
-  argmax_rows_kernel<<<(N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(logits, dst, N, K);
+  TLXCV_LAUNCH(argmax_rows_kernel, (N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st, logits, dst, N, K);
   return cudaGetLastError();
 }
 

@@ -192,6 +192,8 @@ stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();               // the previous kernel's output (the padded input) is complete and visible from here on
+  pdl_launch_dependents();  // the next kernel may take this SM as soon as this CTA exits
 
   if (warp == 0) {
     // ===================== TMA producer: weights once, then one group of 2*sv input rows per step =====================
@@ -460,6 +462,7 @@ __global__ void pack_stem_weights_kernel(const float* __restrict__ w, __nv_bfloa
 // NCHW fp32 (C <= 4) -> [N][H][Wp][4] bf16 with zero pad columns
 __global__ void import_nchw_c4_padded_kernel(const float* __restrict__ src, uint2* __restrict__ dst, int C, int H, int W,
                                              int Wp, int pad_l, size_t total) {
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int wp = static_cast<int>(idx % Wp);
@@ -482,6 +485,7 @@ __global__ void import_nchw_c4_padded_kernel(const float* __restrict__ src, uint
 // needs W % 4 == 0, pad_l % 4 == 0, Wp % 4 == 0 so that no group of 4 straddles the image edge
 __global__ void import_nchw_c4_padded_x4_kernel(const float* __restrict__ src, uint4* __restrict__ dst, int C, int H, int W,
                                                 int Wp4, int pad_l, size_t total) {
+  pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int wq = static_cast<int>(idx % Wp4);
@@ -591,13 +595,12 @@ cudaError_t pack_stem_weights(const float* oihw, __nv_bfloat16* dst, int Cout, i
 cudaError_t import_nchw_c4_padded(const float* src, void* dst, int N, int C, int H, int W, int Wp, int pad_l, cudaStream_t st) {
   if (W % 4 == 0 && pad_l % 4 == 0 && Wp % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {
     const size_t total = static_cast<size_t>(N) * H * (Wp / 4);
-    import_nchw_c4_padded_x4_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, static_cast<uint4*>(dst), C, H, W,
-                                                                                                 Wp / 4, pad_l, total);
-    return cudaGetLastError();
+    return launch_pdl(import_nchw_c4_padded_x4_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, src,
+                      static_cast<uint4*>(dst), C, H, W, Wp / 4, pad_l, total);
   }
   const size_t total = static_cast<size_t>(N) * H * Wp;
-  import_nchw_c4_padded_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(src, static_cast<uint2*>(dst), C, H, W, Wp, pad_l, total);
-  return cudaGetLastError();
+  return launch_pdl(import_nchw_c4_padded_kernel, static_cast<unsigned>((total + 255) / 256), 256, 0, st, src,
+                    static_cast<uint2*>(dst), C, H, W, Wp, pad_l, total);
 }
 
 std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry& g, const __nv_bfloat16* in_padded, int N,
@@ -687,8 +690,7 @@ std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry
 cudaError_t stem_rowring_launch(const StemLaunch& L, cudaStream_t st) {
 #define TLXCV_X(BN, RR, SS)                                                                              \
   if (L.block_n == BN && L.p.R == RR && L.p.sv == SS) {                                                  \
-    stem_rowring_kernel<BN, RR, SS><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.p);            \
-    return cudaGetLastError();                                                                           \
+    return launch_pdl(stem_rowring_kernel<BN, RR, SS>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.p); \
   }
   TLXCV_STEM_INSTANCES(TLXCV_X)
 #undef TLXCV_X
