@@ -216,6 +216,76 @@ def test_stem_with_fused_maxpool_bf16(hw, neg):
         assert float(fused.max()) < 0
 
 
+@pytest.mark.parametrize("cin,mid,cout,hw,stride,n", [(64, 32, 128, 16, 1, 3), (256, 128, 512, 14, 2, 2), (64, 64, 256, 9, 1, 5),
+                                                       (72, 40, 136, 12, 2, 2)])
+def test_bottleneck_tail_and_downsample_run_as_one_dual_gemm_kernel(cin, mid, cout, hw, stride, n):
+    """relu(bn3(conv3(h)) + bn_d(conv_d(x))) of a stage's first block (resnet.py:142-156, :246-261): one kernel with two
+    TMEM accumulators; must agree with the unfused pipeline (TLXCV_NO_DUAL) and with fp32 math on bf16-rounded operands."""
+    from tlxcv_b200 import nn, runtime
+
+    g = torch.Generator().manual_seed(cin + hw)
+    x = torch.randn(n, cin, hw, hw, generator=g)
+
+    def bn_params(c):
+        return dict(beta=torch.randn(c, generator=g) * 0.1, gamma=0.75 + 0.5 * torch.rand(c, generator=g),
+                    moving_mean=torch.randn(c, generator=g) * 0.1, moving_var=0.75 + 0.5 * torch.rand(c, generator=g))
+
+    w2 = torch.randn(mid, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    w3 = torch.randn(cout, mid, 1, 1, generator=g) * (1.0 / mid) ** 0.5
+    wd = torch.randn(cout, cin, 1, 1, generator=g) * (1.0 / cin) ** 0.5
+    b2, b3, bd = bn_params(mid), bn_params(cout), bn_params(cout)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv2 = nn.GroupConv2d(in_channels=cin, out_channels=mid, kernel_size=3, stride=stride, padding=1, b_init=None)
+            self.bn2 = nn.BatchNorm2d(num_features=mid)
+            self.conv3 = nn.GroupConv2d(in_channels=mid, out_channels=cout, kernel_size=1, stride=1, padding=0, b_init=None)
+            self.bn3 = nn.BatchNorm2d(num_features=cout)
+            self.convd = nn.GroupConv2d(in_channels=cin, out_channels=cout, kernel_size=1, stride=stride, padding=0, b_init=None)
+            self.bnd = nn.BatchNorm2d(num_features=cout)
+            self.relu = nn.ReLU()
+
+        def forward(self, x):
+            out = self.relu(self.bn2(self.conv2(x)))
+            out = self.bn3(self.conv3(out))
+            identity = self.bnd(self.convd(x))
+            out += identity
+            return self.relu(out)
+
+    sd = {"conv2.filters": w2, "conv3.filters": w3, "convd.filters": wd}
+    for name, b in (("bn2", b2), ("bn3", b3), ("bnd", bd)):
+        sd.update({f"{name}.{k}": v for k, v in b.items()})
+
+    def run():
+        net = Net()
+        net.load_state_dict(sd)
+        net = net.cuda().set_eval()
+        plan, _, flat = runtime.get_plan(net, (x.cuda(),), {})
+        return plan.run(flat, graph=False)[0].cpu(), [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))], plan.num_launches
+
+    os.environ["TLXCV_FORCE_DUAL"] = "1"      # also exercise shapes the planner would leave unfused (deep K)
+    try:
+        fused, kernels, launches = run()
+    finally:
+        del os.environ["TLXCV_FORCE_DUAL"]
+    assert "conv_tcgen05_dual_n128" in kernels, kernels
+    os.environ["TLXCV_NO_DUAL"] = "1"
+    try:
+        unfused, kernels2, launches2 = run()
+    finally:
+        del os.environ["TLXCV_NO_DUAL"]
+    assert "conv_tcgen05_dual_n128" not in kernels2 and launches2 == launches + 1
+    q = lambda t: t.bfloat16().float()
+    bn = lambda t, b: F.batch_norm(t, b["moving_mean"], b["moving_var"], b["gamma"], b["beta"], False, 0.0, 1e-5)
+    h = q(F.relu(bn(F.conv2d(q(x), q(w2), None, stride, 1), b2)))
+    y = F.relu(bn(F.conv2d(h, q(w3)), b3) + bn(F.conv2d(q(x), q(wd), None, stride), bd))
+    tol = 2.0 ** -7 * max(1.0, float(y.abs().max()))
+    assert fused.shape == y.shape
+    assert float((fused - y).abs().max()) <= tol
+    assert float((unfused - y).abs().max()) <= 2 * tol      # the unfused pipeline rounds the downsample map to bf16 once more
+
+
 def test_maxpool_gap_linear_argmax_small():
     """Stem + MaxPool2d(3,2,1) + GAP + Linear + argmax on their own (fp32 mode: exact semantics, incl. -inf pool padding)."""
     import tlxcv_b200 as tlx

@@ -104,6 +104,8 @@ struct EpiArgs {
   const float* sc_cache;  // smem 2 x [scale(256) | shift(256)]: filled once when the layer has a single N tile (sc_static),
                           // else buffer [acc] is refreshed by the epilogue warps for every tile
   int sc_mode;  // 0: smem buffer filled once; 1: smem buffer [acc] refreshed per tile; 2: global loads per chunk
+  const float* scale2;  // DUAL: folded BN of the second accumulator
+  const float* shift2;
   const float* scale;
   const float* shift;
   float* out_f32;
@@ -130,9 +132,14 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // items ahead; each lane reads ITS row of the buffer, computes, and writes its output row back into
 // the same buffer, which one TMA store then drains.  No per-element global addressing, no
 // predicates: TMA clips the M and C_out tails.
-template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing>
+// DUAL: the tile has TWO accumulators (conv3 of a bottleneck and the block's downsample conv, see the kernel):
+//     y = act1( acc1 * scale + shift  +  acc2 * scale2 + shift2 )
+// the scale/shift buffer then holds [scale | scale2 | shift | shift2] for the tile's BLOCK_N = 128 channels.
+template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool DUAL = false>
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
   static_assert(!RES || kRing == 4, "the residual prefetch runs three items ahead");
+  static_assert(!DUAL || (BLOCK_N == 128 && !RES && !F32), "dual accumulators: 128-wide bf16 tiles without a residual");
+  constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
   constexpr int kCpw = (BLOCK_N / 32) / 2;  // chunks per warp per tile
   const int c_first = cgroup * kCpw;
   const int swz_own = (lane >> 1) & 3;
@@ -176,11 +183,15 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = min(kCpw, max(0, (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
-    float4 sc_pf = make_float4(0.f, 0.f, 0.f, 0.f), sh_pf = sc_pf;
+    float4 sc_pf = make_float4(0.f, 0.f, 0.f, 0.f), sh_pf = sc_pf, sc2_pf = sc_pf, sh2_pf = sc_pf;
     if (a.sc_mode == 1 && lane < kCpw * 8) {
       // this warp's slice of the tile's scale / shift: fetched now, the latency hides behind the accumulator wait
       sc_pf = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + c_first * 32) + lane);
       sh_pf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + c_first * 32) + lane);
+      if (DUAL) {
+        sc2_pf = __ldg(reinterpret_cast<const float4*>(a.scale2 + n0 + c_first * 32) + lane);
+        sh2_pf = __ldg(reinterpret_cast<const float4*>(a.shift2 + n0 + c_first * 32) + lane);
+      }
     }
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
@@ -193,6 +204,10 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       if (lane < kCpw * 8) {
         reinterpret_cast<float4*>(sc_buf + c_first * 32)[lane] = sc_pf;
         reinterpret_cast<float4*>(sc_buf + 256 + c_first * 32)[lane] = sh_pf;
+        if (DUAL) {
+          reinterpret_cast<float4*>(sc_buf + 128 + c_first * 32)[lane] = sc2_pf;
+          reinterpret_cast<float4*>(sc_buf + 384 + c_first * 32)[lane] = sh2_pf;
+        }
       }
       __syncwarp();
     }
@@ -203,7 +218,10 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       const int cbase = n0 + chunk * 32;
       const uint32_t slot = it & (kRing - 1);
       uint32_t v[32];
-      tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * BLOCK_N + chunk * 32, v);
+      tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + chunk * 32, v);
+      uint32_t v2[DUAL ? 32 : 1];
+      if (DUAL) tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + BLOCK_N + chunk * 32,
+                                   reinterpret_cast<uint32_t(&)[32]>(v2));
       if (RES) {
         mbar_wait(a.res_bar + slot * 8, (it / kRing) & 1);  // residual chunk has landed in the ring slot
       } else if (!F32) {
@@ -218,7 +236,21 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       }
       tmem_ld_wait();
       float f[32];
-      if (a.sc_mode != 2) {
+      if (DUAL) {
+        // sum of the two folded-BN branches in fp32, then the block's activation
+        const float4* s1p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + chunk * 32 : a.scale + cbase);
+        const float4* h1p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + 256 + chunk * 32 : a.shift + cbase);
+        const float4* s2p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + 128 + chunk * 32 : a.scale2 + cbase);
+        const float4* h2p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + 384 + chunk * 32 : a.shift2 + cbase);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const float4 s1 = s1p[j], h1 = h1p[j], s2 = s2p[j], h2 = h2p[j];
+          f[4 * j + 0] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 0]), s1.x, h1.x) + fmaf(__uint_as_float(v2[(4 * j + 0) % (DUAL ? 32 : 1)]), s2.x, h2.x), a.alpha1);
+          f[4 * j + 1] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 1]), s1.y, h1.y) + fmaf(__uint_as_float(v2[(4 * j + 1) % (DUAL ? 32 : 1)]), s2.y, h2.y), a.alpha1);
+          f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), s1.z, h1.z) + fmaf(__uint_as_float(v2[(4 * j + 2) % (DUAL ? 32 : 1)]), s2.z, h2.z), a.alpha1);
+          f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), s1.w, h1.w) + fmaf(__uint_as_float(v2[(4 * j + 3) % (DUAL ? 32 : 1)]), s2.w, h2.w), a.alpha1);
+        }
+      } else if (a.sc_mode != 2) {
         const float4* scp = reinterpret_cast<const float4*>(sc_buf + chunk * 32);
         const float4* shp = reinterpret_cast<const float4*>(sc_buf + 256 + chunk * 32);
 #pragma unroll
@@ -302,12 +334,22 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   if (!F32 && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
-template <int BLOCK_N, int MODE>
+// DUAL (BLOCK_N = 128, MODE = kModeTiled): two GEMMs per output tile into two TMEM accumulators,
+//   acc1 = A[M][K1] * W1^T   (K blocks 0 .. num_kb1-1: tmapA / tmapB, the bottleneck's last 1x1 conv)
+//   acc2 = A2      * W2^T   (remaining K blocks: tmapA2 / tmapB2, the block's 1x1 stride-s downsample conv read
+//                            either as a plain [M][C2] matrix (s = 1) or through im2col-mode TMA (s = 2)),
+// combined by the epilogue.  It replaces `out = relu(bn3(conv3(x2)) + bn_d(conv_d(x)))` of a ResNet / ResNeXt
+// stage's first block (classification/resnet.py:142-156, :246-261) without the downsample map ever reaching HBM.
+template <int BLOCK_N, int MODE, bool DUAL = false>
 __global__ void __launch_bounds__(MODE == kModeGatherC4 ? kThreadsGather : kThreadsBase, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapOut, const __grid_constant__ CUtensorMap tmapRes,
+                    const __grid_constant__ CUtensorMap tmapA2, const __grid_constant__ CUtensorMap tmapB2,
                     const ConvKernelParams p) {
   using C = Cfg<BLOCK_N>;
+  static_assert(!DUAL || (BLOCK_N == 128 && MODE == kModeTiled), "dual accumulators: 128-wide tiles over a tiled first operand");
+  constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
+  constexpr int kTmemColsK = 2 * kAccCols;
   // SWIZZLE_128B operand tiles need 1024-byte alignment; no pointer casts through integers here, so
   // that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -331,6 +373,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   if (warp == 1 && lane == 0) {
     if (MODE != kModeGatherC4) tma_prefetch_desc(&tmapA);
     tma_prefetch_desc(&tmapB);
+    if (DUAL) {
+      tma_prefetch_desc(&tmapA2);
+      tma_prefetch_desc(&tmapB2);
+    }
     if (!p.out_f32) tma_prefetch_desc(&tmapOut);
     for (int i = 0; i < n_stages; ++i) {
       mbar_init(smem_u32(&full_bar[i]), MODE == kModeGatherC4 ? 1 + kGatherWarps * 32 : 1);
@@ -344,8 +390,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     if (!p.out_f32 && p.residual != nullptr) tma_prefetch_desc(&tmapRes);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<C::kTmemCols>(smem_u32(tmem_ptr_smem));
-  const bool sc_cached = p.n_tiles == 1;  // one N tile: scale/shift never change, keep them in smem
+  if (warp == 0) tmem_alloc<kTmemColsK>(smem_u32(tmem_ptr_smem));
+  const bool sc_cached = p.n_tiles == 1 && !DUAL;  // one N tile: scale/shift never change, keep them in smem
   if (sc_cached && warp >= 2 && warp < 2 + kEpiWarps) {
     for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiWarps * 32) {
       sc_cache[i] = p.scale[i];
@@ -370,7 +416,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         const int m0 = m_tile * kBlockM, n0 = n_tile * BLOCK_N;
         int img = 0, base_h = 0, base_w = 0;
-        if (MODE == kModeIm2col) {
+        if (MODE == kModeIm2col || (DUAL && p.a2_im2col)) {
           img = m0 / PQ;
           const int rem = m0 - img * PQ;
           const int op = rem / p.Q, oq = rem - op * p.Q;
@@ -385,6 +431,17 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
           const uint32_t a_dst = smem_u32(smem + ps.stage * C::kStageBytes);
           mbar_arrive_expect_tx(bar, MODE == kModeGatherC4 ? C::kBBytes : C::kStageBytes);
+          if (DUAL && kb >= p.num_kb1) {
+            // second GEMM: 1x1 filter, so the K block is just a 64-channel slice of the (strided) input pixels
+            const int kb2 = kb - p.num_kb1;
+            if (p.a2_im2col)
+              tma_load_im2col_4d(a_dst, &tmapA2, bar, kb2 * kBlockK, base_w, base_h, img, 0, 0);
+            else
+              tma_load_2d(a_dst, &tmapA2, bar, kb2 * kBlockK, m0);
+            tma_load_2d(a_dst + kABytes, &tmapB2, bar, kb2 * kBlockK, n0);
+            ps.advance(n_stages);
+            continue;
+          }
           if (MODE == kModeTiled) {
             tma_load_2d(a_dst, &tmapA, bar, kb * kBlockK, m0);
           } else if (MODE == kModeIm2col) {
@@ -413,8 +470,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
         trace_c(p.trace, 1, tr);  // [4k+1] accumulator free
-        const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+        const uint32_t tmem_d1 = tmem_base + acc * kAccCols;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+          const bool second = DUAL && kb >= p.num_kb1;
+          const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
+          const int kbl = second ? kb - p.num_kb1 : kb;  // first K block of an accumulator overwrites it
           mbar_wait(smem_u32(&full_bar[ps.stage]), ps.phase);
           tcgen05_fence_after();
           if (kb == 0) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
@@ -424,7 +484,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            if (!(p.ablate & 4)) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+            if (!(p.ablate & 4)) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kbl | k) != 0);
           }
           umma_commit(smem_u32(&empty_bar[ps.stage]));  // frees the smem stage when these MMAs retire
           ps.advance(n_stages);
@@ -448,6 +508,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.res_bar = smem_u32(res_bar + (warp - 2) * kMaxRing);
     a.sc_cache = sc_cache;
     a.sc_mode = sc_cached ? 0 : (p.sc_bufs == 2 ? 1 : 2);
+    a.scale2 = p.scale2, a.shift2 = p.shift2;
     a.scale = p.scale, a.shift = p.shift;
     a.out_f32 = reinterpret_cast<float*>(p.out);
     a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
@@ -458,6 +519,16 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.trace = p.trace;
     const int lg = warp & 3, cgroup = (warp - 2) >> 2;
     const bool res = kRes && p.residual != nullptr;
+    if constexpr (DUAL) {
+      // the dual tile is a plain (no residual) bf16 tile whose pre-activation value is the sum of both branches
+      if (p.act1 == TLXCV_ACT_RELU) {
+        if (ring == 2) epilogue_loop<BLOCK_N, TLXCV_ACT_RELU, false, TLXCV_ACT_NONE, false, 2, true>(a, lg, cgroup, lane);
+        else epilogue_loop<BLOCK_N, TLXCV_ACT_RELU, false, TLXCV_ACT_NONE, false, 4, true>(a, lg, cgroup, lane);
+      } else {
+        if (ring == 2) epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, false, TLXCV_ACT_NONE, false, 2, true>(a, lg, cgroup, lane);
+        else epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, false, TLXCV_ACT_NONE, false, 4, true>(a, lg, cgroup, lane);
+      }
+    } else {
 #define TLXCV_EPI(A1)                                                                                          \
   if (p.out_f32) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, true, 2>(a, lg, cgroup, lane);              \
   else if (!res && ring == 2) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false, 2>(a, lg, cgroup, lane); \
@@ -471,6 +542,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       default: TLXCV_EPI(TLXCV_ACT_NONE) break;
     }
 #undef TLXCV_EPI
+    }
   } else if (MODE == kModeGatherC4) {
     // ===================== gather producers (C_in <= 4 stems): 8 warps =====================
     // K layout of one 64-wide block: r_per_kb filter rows x KR elements, element = s*4 + c.
@@ -542,7 +614,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc<C::kTmemCols>(tmem_base);
+    tmem_dealloc<kTmemColsK>(tmem_base);
   }
 }
 
@@ -618,16 +690,26 @@ std::string encode_im2col(CUtensorMap* map, const void* base, int N, int H, int 
   return "";
 }
 
-template <int BLOCK_N, int MODE>
+inline int& conv_launch_counter() {
+  static int n = 0;
+  return n;
+}
+
+template <int BLOCK_N, int MODE, bool DUAL = false>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
-  static const char* trace_path = getenv("TLXCV_DEBUG_TRACE_CONV");  // debugging: dump CTA 0's timeline of the LAST conv launch
-  if (trace_path != nullptr) {
+  // debugging: dump CTA 0's timeline of conv launch number TLXCV_DEBUG_TRACE_CONV_INDEX (default: every launch, so the
+  // file holds the last one)
+  static const char* trace_path = getenv("TLXCV_DEBUG_TRACE_CONV");
+  static const int trace_index = getenv("TLXCV_DEBUG_TRACE_CONV_INDEX") ? atoi(getenv("TLXCV_DEBUG_TRACE_CONV_INDEX")) : -1;
+  static int& launch_counter = conv_launch_counter();
+  const int my_index = launch_counter++;
+  if (trace_path != nullptr && (trace_index < 0 || trace_index == my_index)) {
     static unsigned long long* dbuf = nullptr;
     if (!dbuf) cudaMalloc(&dbuf, 3 * kTraceLenC * sizeof(unsigned long long));
     cudaMemsetAsync(dbuf, 0, 3 * kTraceLenC * sizeof(unsigned long long), st);
     ConvKernelParams p = L.p;
     p.trace = dbuf;
-    conv_tcgen05_kernel<BLOCK_N, MODE><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, p);
+    conv_tcgen05_kernel<BLOCK_N, MODE, DUAL><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.tmapA2, L.tmapB2, p);
     cudaStreamSynchronize(st);
     std::vector<unsigned long long> h(3 * kTraceLenC);
     cudaMemcpy(h.data(), dbuf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -637,12 +719,13 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
     }
     return cudaGetLastError();
   }
-  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.p);
+  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
+                    L.tmapRes, L.tmapA2, L.tmapB2, L.p);
 }
 
-template <int BLOCK_N, int MODE>
+template <int BLOCK_N, int MODE, bool DUAL = false>
 cudaError_t set_attr_t() {
-  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               std::max(std::max(Cfg<BLOCK_N>::smem_bytes(2, 1), Cfg<BLOCK_N>::smem_bytes(4, 1)),
                                        std::max(Cfg<BLOCK_N>::smem_bytes(2, 2), Cfg<BLOCK_N>::smem_bytes(4, 2))));
 }
@@ -682,6 +765,7 @@ cudaError_t tc_conv_set_attributes() {
   TLXCV_SET(64, kModeIm2col) TLXCV_SET(128, kModeIm2col) TLXCV_SET(256, kModeIm2col)
   TLXCV_SET(64, kModeGatherC4) TLXCV_SET(128, kModeGatherC4)
 #undef TLXCV_SET
+  if ((e = set_attr_t<128, kModeTiled, true>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -792,10 +876,54 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   } else {
     L.tmapRes = L.tmapB;
   }
+  L.tmapA2 = L.tmapB, L.tmapB2 = L.tmapB;  // only read by dual launches
   return err;
 }
 
+std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloat16* a1, int M, int K1,
+                                 const __nv_bfloat16* w1, const __nv_bfloat16* a2, int N, int H2, int W2, int C2, int stride2,
+                                 const __nv_bfloat16* w2, int Cout, void* out_bf16) {
+  std::string err = load_driver_entry_points();
+  if (!err.empty()) return err;
+  memset(&L, 0, sizeof L);
+  ConvKernelParams& p = L.p;
+  constexpr int block_n = 128;
+  const int P = (H2 - 1) / stride2 + 1, Q = (W2 - 1) / stride2 + 1;
+  if (static_cast<long long>(N) * P * Q != M) return "dual conv: the two branches do not produce the same pixels";
+  if (K1 % 8 || C2 % 8 || Cout % 8) return "dual conv: channel counts must be multiples of 8";
+  p.M = M, p.Cout = Cout;
+  p.S = 1, p.R = 1, p.P = P, p.Q = Q, p.H = H2, p.W = W2, p.stride = stride2, p.pad = 0, p.dil = 1;
+  p.kb_per_tap = 1;
+  p.num_kb1 = (K1 + kBlockK - 1) / kBlockK;
+  p.num_kb = p.num_kb1 + (C2 + kBlockK - 1) / kBlockK;
+  p.a2_im2col = stride2 != 1;
+  p.m_tiles = (M + kBlockM - 1) / kBlockM;
+  p.n_tiles = (Cout + block_n - 1) / block_n;
+  L.mode = kModeTiled, L.block_n = block_n, L.dual = 1, L.threads = kThreadsBase;
+  if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);
+  p.ring = p.num_kb <= 8 ? 4 : 2;
+  p.sc_bufs = stages_for(block_n, p.ring, 2) == stages_for(block_n, p.ring, 1) ? 2 : 1;
+  p.stages = stages_for(block_n, p.ring, p.sc_bufs);
+  L.smem = smem_for(block_n, p.ring, p.sc_bufs);
+  L.grid = static_cast<int>(std::min<long long>(static_cast<long long>(p.m_tiles) * p.n_tiles, sm_count));
+  const int cout_pad = ((Cout + 255) / 256) * 256;
+  const int k1p = p.num_kb1 * kBlockK, k2p = (p.num_kb - p.num_kb1) * kBlockK;
+  if (!(err = encode_2d(&L.tmapB, w1, k1p, cout_pad, static_cast<uint64_t>(k1p) * 2, kBlockK, block_n)).empty()) return err;
+  if (!(err = encode_2d(&L.tmapB2, w2, k2p, cout_pad, static_cast<uint64_t>(k2p) * 2, kBlockK, block_n)).empty()) return err;
+  if (!(err = encode_2d(&L.tmapA, a1, K1, M, static_cast<uint64_t>(K1) * 2, kBlockK, kBlockM)).empty()) return err;
+  if (p.a2_im2col)
+    err = encode_im2col(&L.tmapA2, a2, N, H2, W2, C2, 1, 1, stride2, 0, 1);
+  else
+    err = encode_2d(&L.tmapA2, a2, C2, M, static_cast<uint64_t>(C2) * 2, kBlockK, kBlockM);
+  if (!err.empty()) return err;
+  if (!(err = encode_2d(&L.tmapOut, out_bf16, Cout, M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)).empty())
+    return err;
+  L.tmapRes = L.tmapB;
+  return "";
+}
+
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t st) {
+  if (L.dual) return launch_t<128, kModeTiled, true>(L, st);
 #define TLXCV_CASE(BN, MD) \
   if (L.block_n == BN && L.mode == MD) return launch_t<BN, MD>(L, st);
   TLXCV_CASE(64, kModeTiled) TLXCV_CASE(128, kModeTiled) TLXCV_CASE(256, kModeTiled)

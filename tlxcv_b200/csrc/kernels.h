@@ -45,19 +45,28 @@ struct ConvKernelParams {
   int ablate;  // debug: TLXCV_DEBUG_ABLATE bit mask (timing experiments; 0 in normal operation)
   int stages, ring;  // operand pipeline stages; epilogue store/residual ring depth per warp (2 or 4)
   int sc_bufs;       // scale/shift smem buffers: 1 (filled once, or unused) or 2 (refreshed per tile)
+  // dual-accumulator launches (conv3 + downsample conv of a stage's first block in one kernel)
+  int num_kb1;       // K blocks of the first GEMM (the remaining num_kb - num_kb1 belong to the second)
+  int a2_im2col;     // second A operand: 0 = plain [M][C2] matrix, 1 = im2col-mode TMA (strided 1x1)
+  const float* scale2;
+  const float* shift2;
   unsigned long long* trace;  // debug: TLXCV_DEBUG_TRACE_CONV timeline buffer (NULL in normal operation)
 };
 
 struct TcConvLaunch {
-  CUtensorMap tmapA, tmapB, tmapOut, tmapRes;
+  CUtensorMap tmapA, tmapB, tmapOut, tmapRes, tmapA2, tmapB2;
   ConvKernelParams p;
-  int mode, block_n, grid, threads, smem;
+  int mode, block_n, grid, threads, smem, dual;
 };
 
 // Encodes the TMA descriptors and picks tile shape; returns an empty string or an error message.
 std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
                             int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
                             int pad, int dil, int groups, int force_block_n, void* out_bf16, const void* residual_bf16);
+// out = act( A1[M][K1] * W1^T * scale + shift  +  conv1x1_stride(A2) * W2^T * scale2 + shift2 ): two accumulators per tile
+std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloat16* a1, int M, int K1,
+                                 const __nv_bfloat16* w1, const __nv_bfloat16* a2, int N, int H2, int W2, int C2, int stride2,
+                                 const __nv_bfloat16* w2, int Cout, void* out_bf16);
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
 cudaError_t tc_conv_set_attributes();
 // number of K elements per output channel in the packed weight matrix for this geometry

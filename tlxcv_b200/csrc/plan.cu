@@ -42,6 +42,10 @@ struct OpRt {
   bool use_stem = false;      // row-ring stem kernel chosen in the pre-pass
   int pool_op = -1;           // index of the max-pool op fused into this stem (-1: none)
   bool nop = false;           // fused into another op: no launch, no tensors of its own
+  int dual_a = -1;            // index of the 1x1 conv whose output was this conv's residual and now runs as the
+                              // first accumulator of this op's dual-GEMM kernel (-1: none)
+  float* scale2 = nullptr;    // folded BN of this op's own (second) GEMM in a dual launch (owned)
+  float* shift2 = nullptr;
   void* weights = nullptr;    // packed weights (owned)
   float* scale = nullptr;     // folded BN / bias (owned)
   float* shift = nullptr;
@@ -223,6 +227,53 @@ int compile_stem(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
   char name[48];
   snprintf(name, sizeof name, "stem_rowring_n%d%s%s", g.block_n, g.pairs ? "_pairs" : "", pool ? "_maxpool" : "");
   set_info(op, name, 1, 0, flops, bytes, op.stem.grid, op.stem.threads, op.stem.smem, g.block_n);
+  return TLXCV_OK;
+}
+
+// B = the block's 1x1 (strided) downsample conv, A = the bottleneck's last 1x1 conv whose output was B's residual:
+// one kernel, two TMEM accumulators, out = act2( A-branch + B-branch ) with both folded BNs applied in fp32
+int compile_conv_dual(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
+  tlxcv_ctx* ctx = p->ctx;
+  const tlxcv_op_desc& d = op.d;
+  const tlxcv_op_desc& a = p->ops[op.dual_a].d;
+  const TensorRt& x2 = p->tensors[a.in0];
+  const TensorRt& xin = p->tensors[d.in0];
+  const TensorRt& out = p->tensors[d.out];
+  const int N = xin.d.n, H2 = xin.d.h, W2 = xin.d.w, C2 = xin.d.c, K1 = x2.d.c, K = out.d.c;
+  const long long M = static_cast<long long>(out.d.n) * out.d.h * out.d.w;
+  if (!d.filters || !a.filters) return fail(ctx, TLXCV_ERR_INVALID, "op conv: filters pointer is NULL");
+  if (static_cast<long long>(x2.d.n) * x2.d.h * x2.d.w != M || p->tensors[a.out].d.c != K)
+    return fail(ctx, TLXCV_ERR_INVALID, "dual conv: branch shapes differ");
+  if (x2.d.role != TLXCV_ROLE_INTERNAL || xin.d.role != TLXCV_ROLE_INTERNAL || x2.cs != K1 || xin.cs != C2)
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "dual conv: inputs must be internal dense activation tensors");
+  const int K_pad = static_cast<int>(align_up(K, 256));
+  int rc;
+  if ((rc = dev_alloc(p, &op.scale, K_pad)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.shift, K_pad)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.scale2, K_pad)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.shift2, K_pad)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, fold_bn(op.scale, op.shift, a.bn_gamma, a.bn_beta, a.bn_mean, a.bn_var, a.bias, a.bn_eps, K, K_pad, st));
+  TLX_CUDA(ctx, fold_bn(op.scale2, op.shift2, d.bn_gamma, d.bn_beta, d.bn_mean, d.bn_var, d.bias, d.bn_eps, K, K_pad, st));
+  const int Kt1 = tc_conv_packed_k(K1, 1, 1, 1, kModeTiled), Kt2 = tc_conv_packed_k(C2, 1, 1, 1, kModeTiled);
+  __nv_bfloat16 *w1 = nullptr, *w2 = nullptr;
+  if ((rc = dev_alloc(p, &w1, static_cast<size_t>(K_pad) * Kt1)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &w2, static_cast<size_t>(K_pad) * Kt2)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, pack_conv_weights(a.filters, w1, K, K_pad, K1, 1, 1, 1, kModeTiled, Kt1, st));
+  TLX_CUDA(ctx, pack_conv_weights(d.filters, w2, K, K_pad, C2, 1, 1, 1, kModeTiled, Kt2, st));
+  op.weights = w1;
+  std::string err = tc_conv_prepare_dual(op.tc, ctx->sm_count, reinterpret_cast<const __nv_bfloat16*>(p->arena + x2.offset),
+                                         static_cast<int>(M), K1, w1, reinterpret_cast<const __nv_bfloat16*>(p->arena + xin.offset),
+                                         N, H2, W2, C2, d.stride, w2, K, p->arena + out.offset);
+  if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
+  ConvKernelParams& kp = op.tc.p;
+  kp.scale = op.scale, kp.shift = op.shift, kp.scale2 = op.scale2, kp.shift2 = op.shift2;
+  kp.act1 = d.act2, kp.alpha1 = d.alpha2, kp.act2 = TLXCV_ACT_NONE, kp.alpha2 = 0.0f;
+  kp.out_f32 = 0;
+  op.impl = kImplTcConv;
+  const double flops = 2.0 * M * K * (K1 + C2);
+  const double bytes = (static_cast<double>(M) * (K1 + C2 + K) + static_cast<double>(K) * (K1 + C2)) * 2;
+  set_info(op, "conv_tcgen05_dual_n128", 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.tc.grid, op.tc.threads, op.tc.smem,
+           op.tc.block_n);
   return TLXCV_OK;
 }
 
@@ -562,11 +613,50 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       p->ops[pool].nop = true;
     }
   }
+  // ---- pre-pass: `relu(bn(conv1x1(a)) + bn(conv1x1_stride(b)))` (last conv of a bottleneck + the block's
+  //      downsample conv) becomes ONE dual-accumulator kernel: the residual map never reaches HBM ----
+  if (!p->f32 && !getenv("TLXCV_NO_DUAL")) {
+    for (int i = 0; i < n_ops; ++i) {
+      OpRt& B = p->ops[i];
+      const tlxcv_op_desc& d = B.d;
+      if (B.nop || d.kind != TLXCV_OP_CONV || d.in1 < 0) continue;
+      if (d.r != 1 || d.s != 1 || d.pad != 0 || d.dil != 1 || d.groups != 1 || (d.stride != 1 && d.stride != 2)) continue;
+      if (d.act1 != TLXCV_ACT_NONE || (d.act2 != TLXCV_ACT_NONE && d.act2 != TLXCV_ACT_RELU)) continue;
+      const TensorRt& T = p->tensors[d.in1];
+      const TensorRt& xin = p->tensors[d.in0];
+      const TensorRt& o = p->tensors[d.out];
+      if (T.d.role != TLXCV_ROLE_INTERNAL || T.d.dtype != TLXCV_ACT || o.d.role != TLXCV_ROLE_INTERNAL || o.d.dtype != TLXCV_ACT) continue;
+      if (xin.d.dtype != TLXCV_ACT || xin.d.c % 8 || o.d.c % 8 || xin.d.c <= 4) continue;
+      int producer = -1, users = 0;
+      for (int k = 0; k < n_ops; ++k) {
+        if (p->ops[k].nop) continue;
+        if (p->ops[k].d.out == d.in1) producer = k;
+        if (p->ops[k].d.in0 == d.in1 || p->ops[k].d.in1 == d.in1) ++users;
+      }
+      if (producer < 0 || producer >= i || users != 1) continue;
+      OpRt& A = p->ops[producer];
+      const tlxcv_op_desc& a = A.d;
+      if (a.kind != TLXCV_OP_CONV || a.in1 >= 0 || a.r != 1 || a.s != 1 || a.pad != 0 || a.stride != 1 || a.dil != 1 || a.groups != 1)
+        continue;
+      if (a.act1 != TLXCV_ACT_NONE || a.act2 != TLXCV_ACT_NONE) continue;
+      const TensorRt& x2 = p->tensors[a.in0];
+      if (x2.d.dtype != TLXCV_ACT || x2.d.c % 8 || x2.d.c <= 4) continue;
+      // worth it only while the pair is bound by HBM traffic: the dual kernel works on 128-wide tiles, which costs
+      // the MMA / L2-bound deep stages more than the saved residual round trip brings
+      if ((x2.d.c + 63) / 64 + (xin.d.c + 63) / 64 > 8 && !getenv("TLXCV_FORCE_DUAL")) continue;
+      // a must not be rewritten between A and B (it is read later now): its producer precedes A by construction
+      p->tensors[d.in1].elided = true;
+      A.nop = true;
+      B.dual_a = producer;
+      B.d.in1 = -1;
+    }
+  }
   for (int i = 0; i < n_ops; ++i) {
     OpRt& op = p->ops[i];
     const tlxcv_op_desc& d = op.d;
     if (op.nop) continue;
-    for (int t : {d.in0, d.in1}) {
+    const int extra_in = op.dual_a >= 0 ? p->ops[op.dual_a].d.in0 : -1;
+    for (int t : {d.in0, d.in1, extra_in}) {
       if (t < 0) continue;
       if (p->tensors[t].d.role != TLXCV_ROLE_INPUT && p->tensors[t].first_def < 0)
         return fail(ctx, TLXCV_ERR_INVALID, "op %d reads tensor %d before it is produced", i, t);
@@ -585,7 +675,8 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       if (p->ops[i].nop) continue;
       TensorRt& o = p->tensors[p->ops[i].d.out];
       if (o.d.role == TLXCV_ROLE_INTERNAL) o.offset = arena.alloc(o.bytes);
-      for (int t : {p->ops[i].d.in0, p->ops[i].d.in1, p->ops[i].d.out}) {
+      const int extra_in = p->ops[i].dual_a >= 0 ? p->ops[p->ops[i].dual_a].d.in0 : -1;
+      for (int t : {p->ops[i].d.in0, p->ops[i].d.in1, extra_in, p->ops[i].d.out}) {
         if (t < 0) continue;
         TensorRt& T = p->tensors[t];
         if (!no_reuse && T.d.role == TLXCV_ROLE_INTERNAL && T.last_use == i && T.first_def >= 0) {
@@ -610,7 +701,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     int rc = TLXCV_OK;
     if (op.nop) {
       op.impl = kImplNop;
-      set_info(op, "(fused into the stem conv)", 0, 0, 0, 0, 0, 0, 0, 0);
+      set_info(op, d.kind == TLXCV_OP_CONV ? "(first GEMM of the dual conv)" : "(fused into the stem conv)", 0, 0, 0, 0, 0, 0, 0, 0);
       continue;
     }
     switch (d.kind) {
@@ -629,7 +720,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         break;
       case TLXCV_OP_CONV:
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_ACT) return fail(ctx, TLXCV_ERR_INVALID, "op %d: conv tensors must be activations", i);
-        rc = op.use_stem ? compile_stem(p, op, st) : compile_conv(p, op, st, false);
+        rc = op.use_stem ? compile_stem(p, op, st) : (op.dual_a >= 0 ? compile_conv_dual(p, op, st) : compile_conv(p, op, st, false));
         break;
       case TLXCV_OP_LINEAR:
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_F32 || in.d.h != 1 || in.d.w != 1)
