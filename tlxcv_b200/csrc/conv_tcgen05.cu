@@ -34,15 +34,15 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
-constexpr int kEpiWarps = 8;                    // warps 2..9
-constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
+constexpr int kEpiWarps = 16;                   // warps 2..17; a launch uses p.epi_warps = 8 or 16 of them
+constexpr int kGatherWarps = 8;                 // warps 18..25 (kModeGatherC4 only)
 constexpr int kMaxRing = 4;                     // per epilogue warp: ring of 2 or 4 (32 rows x 64 B) SWIZZLE_64B buffers
 constexpr int kSmemLimit = 232448;              // 227 KB of dynamic shared memory per CTA
 constexpr int kScaleBufBytes = 2 * 256 * 4;      // [scale | shift] of one N tile; the kernel has sc_bufs (1 or 2) of them
-constexpr int kBarrierBytes = 512;              // pipeline barriers + kEpiWarps * kRing residual barriers
+constexpr int kBarrierBytes = 1024;             // pipeline barriers + kEpiWarps * kRing residual barriers
 constexpr int kMaxStages = 8;
-constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
-constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 576
+constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 576
+constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 832
 
 template <int BLOCK_N>
 struct Cfg {
@@ -52,13 +52,14 @@ struct Cfg {
   // smem layout: [stages x (A | B)] [8 warps x ring x 2 KB] [scale cache] [barriers]; the ring depth
   // and therefore the stage count are chosen per layer (deep ring for residual / HBM-bound layers,
   // more operand stages for MMA-bound ones)
-  static constexpr int staging_bytes(int ring) { return kEpiWarps * ring * 2048; }
-  static constexpr int stages_for(int ring, int sc_bufs) {
-    const int n = (kSmemLimit - staging_bytes(ring) - sc_bufs * kScaleBufBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int staging_bytes(int ring, int epi_warps) { return epi_warps * ring * 2048; }
+  static constexpr int stages_for(int ring, int sc_bufs, int epi_warps) {
+    const int n = (kSmemLimit - staging_bytes(ring, epi_warps) - sc_bufs * kScaleBufBytes - kBarrierBytes) / kStageBytes;
     return n > kMaxStages ? kMaxStages : n;
   }
-  static constexpr int smem_bytes(int ring, int sc_bufs) {
-    return stages_for(ring, sc_bufs) * kStageBytes + staging_bytes(ring) + sc_bufs * kScaleBufBytes + kBarrierBytes;
+  static constexpr int smem_bytes(int ring, int sc_bufs, int epi_warps) {
+    return stages_for(ring, sc_bufs, epi_warps) * kStageBytes + staging_bytes(ring, epi_warps) + sc_bufs * kScaleBufBytes +
+           kBarrierBytes;
   }
 };
 
@@ -106,6 +107,7 @@ struct EpiArgs {
   int sc_mode;  // 0: smem buffer filled once; 1: smem buffer [acc] refreshed per tile; 2: global loads per chunk
   const float* scale2;  // DUAL: folded BN of the second accumulator
   const float* shift2;
+  int cpw;
   const float* scale;
   const float* shift;
   float* out_f32;
@@ -137,10 +139,9 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // the scale/shift buffer then holds [scale | scale2 | shift | shift2] for the tile's BLOCK_N = 128 channels.
 template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool DUAL = false>
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
-  static_assert(!RES || kRing == 4, "the residual prefetch runs three items ahead");
   static_assert(!DUAL || (BLOCK_N == 128 && !RES && !F32), "dual accumulators: 128-wide bf16 tiles without a residual");
   constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
-  constexpr int kCpw = (BLOCK_N / 32) / 2;  // chunks per warp per tile
+  const int kCpw = a.cpw;  // chunks per warp per tile: the tile's BLOCK_N / 32 chunks over epi_warps / 4 column groups
   const int c_first = cgroup * kCpw;
   const int swz_own = (lane >> 1) & 3;
   const uint32_t own_row = a.ring + lane * 64;
@@ -152,7 +153,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     const int m_tile = pf_tile / a.n_tiles, n_tile = pf_tile - m_tile * a.n_tiles;
     pf_m0 = m_tile * kBlockM + lg * 32;
     pf_n0 = n_tile * BLOCK_N;
-    pf_nmy = min(kCpw, max(0, (a.Cout - (pf_n0 + c_first * 32) + 31) / 32));
+    pf_nmy = min(min(kCpw, BLOCK_N / 32 - c_first), max(0, (a.Cout - (pf_n0 + c_first * 32) + 31) / 32));
   };
   auto pf_issue = [&]() {  // issue the residual load of the next valid item, if any
     while (pf_tile < a.num_tiles && pf_ci >= pf_nmy) {
@@ -181,10 +182,11 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
     const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
-    const int n_my = min(kCpw, max(0, (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
+    const int n_my = max(0, min(min(kCpw, BLOCK_N / 32 - c_first), (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
     float4 sc_pf = make_float4(0.f, 0.f, 0.f, 0.f), sh_pf = sc_pf, sc2_pf = sc_pf, sh2_pf = sc_pf;
-    if (a.sc_mode == 1 && lane < kCpw * 8) {
+    const bool sc_lane = a.sc_mode == 1 && lane < kCpw * 8 && c_first * 32 + lane * 4 < BLOCK_N;
+    if (sc_lane) {
       // this warp's slice of the tile's scale / shift: fetched now, the latency hides behind the accumulator wait
       sc_pf = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + c_first * 32) + lane);
       sh_pf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + c_first * 32) + lane);
@@ -201,7 +203,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       // Safe to overwrite buffer [acc] now: its previous user (the tile two back) was fully read before every
       // warp released that accumulator (the arrive below comes after the last scale/shift read), and this
       // tile's MMAs could only start after that.  The four warps of a column group write identical values.
-      if (lane < kCpw * 8) {
+      if (sc_lane) {
         reinterpret_cast<float4*>(sc_buf + c_first * 32)[lane] = sc_pf;
         reinterpret_cast<float4*>(sc_buf + 256 + c_first * 32)[lane] = sh_pf;
         if (DUAL) {
@@ -355,7 +357,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int n_stages = p.stages, ring = p.ring;
-  const int staging_bytes = kEpiWarps * ring * 2048;
+  const int epi_warps = p.epi_warps;
+  const int staging_bytes = epi_warps * ring * 2048;
   uint8_t* staging = smem + n_stages * C::kStageBytes;
   float* sc_cache = reinterpret_cast<float*>(staging + staging_bytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + p.sc_bufs * kScaleBufBytes);
@@ -384,7 +387,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), kEpiWarps);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[i]), epi_warps);  // one arrival per epilogue warp
     }
     for (int i = 0; i < kEpiWarps * kMaxRing; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     if (!p.out_f32 && p.residual != nullptr) tma_prefetch_desc(&tmapRes);
@@ -392,8 +395,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   }
   if (warp == 0) tmem_alloc<kTmemColsK>(smem_u32(tmem_ptr_smem));
   const bool sc_cached = p.n_tiles == 1 && !DUAL;  // one N tile: scale/shift never change, keep them in smem
-  if (sc_cached && warp >= 2 && warp < 2 + kEpiWarps) {
-    for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiWarps * 32) {
+  if (sc_cached && warp >= 2 && warp < 2 + epi_warps) {
+    for (int i = threadIdx.x - 64; i < BLOCK_N; i += epi_warps * 32) {
       sc_cache[i] = p.scale[i];
       sc_cache[256 + i] = p.shift[i];
     }
@@ -497,7 +500,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         }
       }
     }
-  } else if (warp < 2 + kEpiWarps) {
+  } else if (warp < 2 + epi_warps) {
     // ===================== epilogue: 8 warps (see epilogue_loop) =====================
     constexpr bool kRes = MODE != kModeGatherC4;  // stems never carry a residual
     EpiArgs a;
@@ -509,6 +512,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.sc_cache = sc_cache;
     a.sc_mode = sc_cached ? 0 : (p.sc_bufs == 2 ? 1 : 2);
     a.scale2 = p.scale2, a.shift2 = p.shift2;
+    a.cpw = max(1, (BLOCK_N / 32) / (epi_warps / 4));
     a.scale = p.scale, a.shift = p.shift;
     a.out_f32 = reinterpret_cast<float*>(p.out);
     a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
@@ -533,7 +537,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   if (p.out_f32) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, true, 2>(a, lg, cgroup, lane);              \
   else if (!res && ring == 2) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false, 2>(a, lg, cgroup, lane); \
   else if (!res) epilogue_loop<BLOCK_N, A1, false, TLXCV_ACT_NONE, false, 4>(a, lg, cgroup, lane);             \
+  else if (p.act2 == TLXCV_ACT_RELU && ring == 2) epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_RELU, false, 2>(a, lg, cgroup, lane); \
   else if (p.act2 == TLXCV_ACT_RELU) epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_RELU, false, 4>(a, lg, cgroup, lane); \
+  else if (ring == 2) epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_NONE, false, 2>(a, lg, cgroup, lane); \
   else epilogue_loop<BLOCK_N, A1, kRes, TLXCV_ACT_NONE, false, 4>(a, lg, cgroup, lane);
     switch (p.act1) {
       case TLXCV_ACT_RELU: TLXCV_EPI(TLXCV_ACT_RELU) break;
@@ -543,7 +549,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
 #undef TLXCV_EPI
     }
-  } else if (MODE == kModeGatherC4) {
+  } else if (MODE == kModeGatherC4 && warp >= 2 + kEpiWarps) {
     // ===================== gather producers (C_in <= 4 stems): 8 warps =====================
     // K layout of one 64-wide block: r_per_kb filter rows x KR elements, element = s*4 + c.
     // Thread -> (A-tile row, 4 of the 8 16-byte chunks of that row): all 8 loads of a K block are
@@ -726,17 +732,38 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
 template <int BLOCK_N, int MODE, bool DUAL = false>
 cudaError_t set_attr_t() {
   return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              std::max(std::max(Cfg<BLOCK_N>::smem_bytes(2, 1), Cfg<BLOCK_N>::smem_bytes(4, 1)),
-                                       std::max(Cfg<BLOCK_N>::smem_bytes(2, 2), Cfg<BLOCK_N>::smem_bytes(4, 2))));
+                              kSmemLimit);
 }
 
-int smem_for(int block_n, int ring, int sc_bufs) {
-  return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs)
-                        : (block_n == 128 ? Cfg<128>::smem_bytes(ring, sc_bufs) : Cfg<64>::smem_bytes(ring, sc_bufs));
+int smem_for(int block_n, int ring, int sc_bufs, int ew) {
+  return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs, ew)
+                        : (block_n == 128 ? Cfg<128>::smem_bytes(ring, sc_bufs, ew) : Cfg<64>::smem_bytes(ring, sc_bufs, ew));
 }
-int stages_for(int block_n, int ring, int sc_bufs) {
-  return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs)
-                        : (block_n == 128 ? Cfg<128>::stages_for(ring, sc_bufs) : Cfg<64>::stages_for(ring, sc_bufs));
+int stages_for(int block_n, int ring, int sc_bufs, int ew) {
+  return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs, ew)
+                        : (block_n == 128 ? Cfg<128>::stages_for(ring, sc_bufs, ew) : Cfg<64>::stages_for(ring, sc_bufs, ew));
+}
+
+// Epilogue configuration of a launch: 8 epilogue warps; a 4-deep store / residual ring for residual layers and for
+// layers with few K blocks per tile (epilogue / HBM bound), a 2-deep ring for MMA-bound layers, which need the shared
+// memory for operand stages instead.  16 epilogue warps (TLXCV_DEBUG_EPI_WARPS=16) were measured on B200 and are NOT
+// faster: ResNet-50 bs256 3.67 ms against 3.51 ms - the per-SM epilogue rate is set by shared-memory traffic (staging
+// stores, TMA store reads, scale/shift broadcasts next to the MMA operand reads) and the per-chunk proxy fence, not by
+// the number of warps issuing.
+void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_bf16) {
+  static const int force = getenv("TLXCV_DEBUG_EPI_WARPS") ? atoi(getenv("TLXCV_DEBUG_EPI_WARPS")) : 0;
+  const bool light = p.num_kb <= 8;
+  p.epi_warps = 8;
+  if (force == 8 || force == 16) p.epi_warps = force;
+  if (block_n == 64 && p.epi_warps == 16) p.epi_warps = 8;  // two 32-column chunks per tile: nothing for 16 warps to share
+  p.ring = 2;
+  if (p.epi_warps == 8 && (residual || light)) p.ring = 4;
+  if (!out_bf16) p.ring = 2;
+  // scale/shift: one smem buffer filled once (single N tile); two buffers refreshed per tile by the epilogue
+  // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
+  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps) == stages_for(block_n, p.ring, 1, p.epi_warps)) ? 2 : 1;
+  if (const char* e = getenv("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
+  p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps);
 }
 
 }  // namespace
@@ -836,14 +863,8 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // residual layers and short-K (HBM / epilogue bound) layers get the deep store ring; long-K
   // (MMA bound) layers trade it for one more operand stage
   if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only: results are wrong
-  p.ring = (residual_bf16 != nullptr || p.num_kb <= 8) ? 4 : 2;
-  if (!out_bf16) p.ring = 2;
-  // scale/shift: one smem buffer filled once (single N tile); two buffers refreshed per tile by the epilogue
-  // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
-  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2) == stages_for(block_n, p.ring, 1)) ? 2 : 1;
-  if (const char* e = getenv("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
-  p.stages = stages_for(block_n, p.ring, p.sc_bufs);
-  L.smem = smem_for(block_n, p.ring, p.sc_bufs);
+  choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr);
+  L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps);
   const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
   L.grid = static_cast<int>(std::min<long long>(tiles, sm_count));
 
@@ -901,10 +922,12 @@ std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloa
   p.n_tiles = (Cout + block_n - 1) / block_n;
   L.mode = kModeTiled, L.block_n = block_n, L.dual = 1, L.threads = kThreadsBase;
   if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);
-  p.ring = p.num_kb <= 8 ? 4 : 2;
-  p.sc_bufs = stages_for(block_n, p.ring, 2) == stages_for(block_n, p.ring, 1) ? 2 : 1;
-  p.stages = stages_for(block_n, p.ring, p.sc_bufs);
-  L.smem = smem_for(block_n, p.ring, p.sc_bufs);
+  choose_epilogue(p, block_n, false, true);
+  if (p.sc_bufs != 2 && stages_for(block_n, p.ring, 2, p.epi_warps) >= 2) {  // the dual epilogue reads four vectors: keep them in smem
+    p.sc_bufs = 2;
+    p.stages = stages_for(block_n, p.ring, 2, p.epi_warps);
+  }
+  L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps);
   L.grid = static_cast<int>(std::min<long long>(static_cast<long long>(p.m_tiles) * p.n_tiles, sm_count));
   const int cout_pad = ((Cout + 255) / 256) * 256;
   const int k1p = p.num_kb1 * kBlockK, k2p = (p.num_kb - p.num_kb1) * kBlockK;

@@ -45,6 +45,7 @@ struct ConvKernelParams {
   int ablate;  // debug: TLXCV_DEBUG_ABLATE bit mask (timing experiments; 0 in normal operation)
   int stages, ring;  // operand pipeline stages; epilogue store/residual ring depth per warp (2 or 4)
   int sc_bufs;       // scale/shift smem buffers: 1 (filled once, or unused) or 2 (refreshed per tile)
+  int epi_warps;     // epilogue warps taking part: 8 or 16
   // dual-accumulator launches (conv3 + downsample conv of a stage's first block in one kernel)
   int num_kb1;       // K blocks of the first GEMM (the remaining num_kb - num_kb1 belong to the second)
   int a2_im2col;     // second A operand: 0 = plain [M][C2] matrix, 1 = im2col-mode TMA (strided 1x1)
