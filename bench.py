@@ -35,6 +35,19 @@ METRIC = "resnet50_bs256_images_per_sec"
 UNIT = "images/s"
 
 
+TENSOR_KERNELS = ("conv_tcgen05", "conv3x3_slab", "stem_rowring")
+
+
+def load_ncu_traffic():
+    """DRAM bytes (read + write) of the tensor-core conv family per step, from the committed ncu pass
+    (tools/ncu_round.sh -> tools/ncu_summary.py -> profiles/ncu_traffic.json); None when no capture is committed."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        return float(json.load(open(p))["conv_family_dram_bytes_per_step"])
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def load_peaks():
     peaks = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "source": "fallback"}
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -242,14 +255,15 @@ def main():
         prof = None
         for _ in range(3):
             prof = plan.profile([x_dev], logits)
-        conv = [p for p in prof if p["kernel"].startswith("conv_tcgen05")]
+        conv = [p for p in prof if p["kernel"].startswith(TENSOR_KERNELS)]
         flops = sum(p["flops"] for p in conv)
         conv_ms = sum(p["ms"] for p in conv)
         all_ms = sum(p["ms"] for p in prof)
         achieved = flops / (conv_ms * 1e-3) / 1e12
         roof = {"bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                "frac": achieved / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
-                "kernel": "conv_tcgen05_* (53 conv + fc launches per step)", "launches_per_step": len(conv),
+                "frac": achieved / peaks["bf16_tflops"], "traffic": load_ncu_traffic(), "peak_source": peaks["source"],
+                "kernel": "tcgen05 conv family: conv_tcgen05_* / conv3x3_slab / stem_rowring (all conv + fc launches of a step)",
+                "launches_per_step": len(conv),
                 "flops_per_step": flops, "kernel_ms_per_step": conv_ms, "share_of_step": conv_ms / all_ms,
                 "hbm_bound_layers": sum(1 for p in conv if p["bound"] == "hbm"),
                 "algorithmic_bytes_per_step": sum(p["bytes"] for p in conv)}

@@ -67,5 +67,33 @@ def main():
                   f"{d.get('lts__t_bytes.sum', 0) / 1e6:9.1f} {(tp[0] if tp else 0):8.1f}")
 
 
+def traffic_json(path, out_json):
+    """Per-step DRAM traffic of the tensor-core conv family from the traffic pass (-k filter; 4 forwards of one plan)."""
+    import json
+    tr = read(path)
+    per = OrderedDict()
+    for r in tr:
+        d = per.setdefault(r["ID"], {"kernel": short(r["Kernel Name"])})
+        v = float(r["Metric Value"].replace(",", ""))
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1.0)
+        d[r["Metric Name"]] = v * scale
+    fam = ("conv_tcgen05", "conv3x3_slab", "stem_rowring")
+    ids = list(per.values())
+    # one step = the launches between two consecutive import kernels
+    starts = [i for i, d in enumerate(ids) if d["kernel"].startswith("import_nchw")]
+    if len(starts) < 2:
+        return
+    step = ids[starts[0]:starts[1]]
+    conv = [d for d in step if d["kernel"].startswith(fam)]
+    tot = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in conv)
+    allb = sum(d.get("dram__bytes_read.sum", 0) + d.get("dram__bytes_write.sum", 0) for d in step)
+    json.dump({"source": path, "launches_per_step": len(step), "conv_family_launches_per_step": len(conv),
+               "conv_family_dram_bytes_per_step": tot, "all_kernels_dram_bytes_per_step": allb,
+               "note": "dram__bytes_read.sum + dram__bytes_write.sum per launch (ncu, cold caches, serialised), summed over "
+                       "the conv-family launches of one forward"}, open(out_json, "w"), indent=1)
+
+
 if __name__ == "__main__":
     main()
+    if len(sys.argv) > 3:
+        traffic_json(sys.argv[2], sys.argv[3])
