@@ -132,6 +132,13 @@ LAYERS = {
                                    "conv_tcgen05_im2col"),
     "im2col_odd_size_19": (dict(n=1, cin=64, hw=19, cout=128, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col"),
     "grouped_g32_c128": (dict(n=2, cin=128, hw=14, cout=128, k=3, stride=1, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
+    "grouped_g32_c128_w21": (dict(n=2, cin=128, hw=21, cout=128, k=3, stride=1, pad=1, groups=32, act="relu"), "conv3x3_slab_grouped"),
+    "grouped_g32_c256_w28": (dict(n=3, cin=256, hw=28, cout=256, k=3, stride=1, pad=1, groups=32, act="relu"), "conv3x3_slab_grouped"),
+    "grouped_g32_c128_w56": (dict(n=2, cin=128, hw=56, cout=128, k=3, stride=1, pad=1, groups=32, act="relu"), "conv3x3_slab_grouped"),
+    "grouped_g32_c512_cpg16_w24": (dict(n=2, cin=512, hw=24, cout=512, k=3, stride=1, pad=1, groups=32, act="relu"), "conv3x3_slab_grouped"),
+    "slab_c32_leaky_residual_w40": (dict(n=2, cin=32, hw=40, cout=64, k=3, stride=1, pad=1, act="leaky", res=True), "conv3x3_slab_c32"),
+    "slab_c32_three_segments_w304": (dict(n=1, cin=32, hw=304, cout=64, k=3, stride=1, pad=1, act="leaky", res=True), "conv3x3_slab_c32"),
+    "slab_c64_two_segments_w130_residual_relu": (dict(n=1, cin=64, hw=130, cout=64, k=3, stride=1, pad=1, act="relu", res=True, act2="relu"), "conv3x3_slab"),
     "grouped_g32_c256_s2": (dict(n=2, cin=256, hw=14, cout=256, k=3, stride=2, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
     "grouped_g32_c1024": (dict(n=1, cin=1024, hw=7, cout=1024, k=3, stride=1, pad=1, groups=32, act="relu"), "conv_tcgen05_im2col"),
     "depthwise_s1": (dict(n=2, cin=32, hw=14, cout=32, k=3, stride=1, pad=1, groups=32, act="relu6"), "dwconv"),

@@ -34,21 +34,20 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
-constexpr int kEpiWarps = 16;                   // warps 2..17; a launch uses p.epi_warps = 8 or 16 of them
-constexpr int kGatherWarps = 8;                 // warps 18..25 (kModeGatherC4 only)
+constexpr int kEpiWarps = 8;                    // warps 2..9 (raise to 16 to experiment with p.epi_warps = 16: costs registers)
+constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
 constexpr int kMaxRing = 4;                     // per epilogue warp: ring of 2 or 4 (32 rows x 64 B) SWIZZLE_64B buffers
 constexpr int kSmemLimit = 232448;              // 227 KB of dynamic shared memory per CTA
 constexpr int kScaleBufBytes = 2 * 256 * 4;      // [scale | shift] of one N tile; the kernel has sc_bufs (1 or 2) of them
 constexpr int kBarrierBytes = 1024;             // pipeline barriers + kEpiWarps * kRing residual barriers
 constexpr int kMaxStages = 8;
-constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 576
-constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 832
+constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
+constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 576
 
 template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N;  // 128 / 256 / 512: a power of two >= 32
   // smem layout: [stages x (A | B)] [8 warps x ring x 2 KB] [scale cache] [barriers]; the ring depth
   // and therefore the stage count are chosen per layer (deep ring for residual / HBM-bound layers,
   // more operand stages for MMA-bound ones)
@@ -754,7 +753,7 @@ void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_b
   static const int force = getenv("TLXCV_DEBUG_EPI_WARPS") ? atoi(getenv("TLXCV_DEBUG_EPI_WARPS")) : 0;
   const bool light = p.num_kb <= 8;
   p.epi_warps = 8;
-  if (force == 8 || force == 16) p.epi_warps = force;
+  if (force == 8 || (force == 16 && kEpiWarps >= 16)) p.epi_warps = force;
   if (block_n == 64 && p.epi_warps == 16) p.epi_warps = 8;  // two 32-column chunks per tile: nothing for 16 warps to share
   p.ring = 2;
   if (p.epi_warps == 8 && (residual || light)) p.ring = 4;

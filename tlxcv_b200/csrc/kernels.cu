@@ -56,7 +56,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
       const int cpg_out = Cout / groups;
       if (c < Cin && c / Cg == o / cpg_out) v = w[((static_cast<size_t>(o) * Cg + (c % Cg)) * R + r) * S + s];
     } else {
-      const int kpt = ((Cin + 63) / 64) * 64;
+      const int kpt = mode == kModeSlabDense ? Cin : ((Cin + 63) / 64) * 64;
       const int tap = k / kpt, c = k % kpt;
       const int r = tap / S, s = tap % S;
       if (c < Cin) v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s];

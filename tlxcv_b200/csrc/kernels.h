@@ -16,7 +16,8 @@ namespace tlxcv {
 enum ConvMode : int {
   kModeTiled = 0,   // 1x1 stride-1: A = [M][C] plain 2-D TMA tiles
   kModeIm2col = 1,  // general RxS / stride / pad: A tiles by im2col-mode TMA from NHWC
-  kModeGatherC4 = 2 // C_in <= 4 stems: producer warps gather from NHWC4 into the swizzled A tile
+  kModeGatherC4 = 2, // C_in <= 4 stems: producer warps gather from NHWC4 into the swizzled A tile
+  kModeSlabDense = 3 // weight packing only: K = taps x exactly C_in channels (conv3x3_slab.cu, dense layers)
 };
 
 struct ConvKernelParams {
@@ -128,16 +129,21 @@ cudaError_t import_nchw_c4_padded(const float* src, void* dst, int N, int C, int
 
 // ---- 3x3 stride-1 conv with 64 input channels as a slab implicit GEMM (conv3x3_slab.cu) -----------
 struct SlabParams {
-  int N, H, W;
-  int T;                 // output rows per step = floor(128 / (W + 2))
+  int N, H, W, Cout;
+  int cblocks;           // 64-channel blocks worked on independently (grouped conv), 1 for a dense layer
+  int segs, Ws;          // column segments per row and their width (Ws + 2 <= 128 slab pixels with the halo)
+  int T;                 // output rows per step = floor(128 / (Ws + 2))
+  int ng;                // row groups a step's window spans: 1 + ceil(2 / T)
   int NG;                // ring depth in groups of T input rows
   int bands, band_rows;  // bands per image; output rows per band
-  const __nv_bfloat16* in;  // NHWC input (L2 prefetch addresses; operand loads go through tmapA)
-  __nv_bfloat16* out;       // NHWC output
+  __nv_bfloat16* out;       // NHWC output (all Cout channels; an item writes its 64-channel block)
+  const __nv_bfloat16* residual;  // NHWC, Cout channels, or NULL:  y = act2(act(acc * scale + shift) + residual)
   const float* scale;
   const float* shift;
   int act;
   float alpha;
+  int act2;
+  float alpha2;
   int ablate;  // debug: TLXCV_DEBUG_ABLATE_SLAB bit mask (timing experiments; 0 in normal operation)
   unsigned long long* trace;  // debug: TLXCV_DEBUG_TRACE_SLAB timeline buffer (NULL in normal operation)
 };
@@ -145,13 +151,14 @@ struct SlabParams {
 struct SlabLaunch {
   CUtensorMap tmapA, tmapB;
   SlabParams p;
-  int block_n, grid, threads, smem;
+  int block_n, cb, grid, threads, smem;
 };
 
-bool conv3x3_slab_supported(int Cin, int Cout, int H, int W, int R, int S, int stride, int pad, int dil, int groups,
-                            bool residual);
-std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat16* in, int N, int H, int W, int Cout,
-                                 const __nv_bfloat16* packed_w, int Ktot, void* out);
+bool conv3x3_slab_supported(int Cin, int Cout, int H, int W, int R, int S, int stride, int pad, int dil, int groups);
+// packed_w: [Cout_pad][9 x CB] with K order (tap, channel of the block): dense layers CB = Cin (kModeSlabDense packing),
+// grouped layers CB = 64 with the block-diagonal expansion of the grouped packing
+std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat16* in, int N, int H, int W, int Cin, int Cout,
+                                 int groups, const __nv_bfloat16* packed_w, int Ktot, void* out, const void* residual);
 cudaError_t conv3x3_slab_launch(const SlabLaunch& L, cudaStream_t st);
 cudaError_t conv3x3_slab_set_attributes();
 

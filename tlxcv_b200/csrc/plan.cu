@@ -369,16 +369,22 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   }
   if (d.act2 != TLXCV_ACT_NONE && d.act2 != TLXCV_ACT_RELU)
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: only ReLU (or nothing) may follow the residual add on the tensor-core path");
-  if (!is_linear && out_bf16 && in.cs == C &&
-      conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups, d.in1 >= 0 || d.act2 != TLXCV_ACT_NONE)) {
-    // wide 3x3 stride-1 layer: slab kernel (each input row fetched once, stationary weights)
-    std::string serr = conv3x3_slab_prepare(op.slab, ctx->sm_count, act_in, N, H, W, K, w, Ktot, out_bf16);
+  if (!is_linear && out_bf16 && in.cs == C && conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups)) {
+    // 3x3 stride-1 layer with 64-channel work items: slab kernel (each input row fetched once, stationary weights)
+    __nv_bfloat16* ws = w;
+    int Kts = Ktot;
+    if (groups == 1) {  // dense: K = 9 taps x exactly C channels
+      Kts = 9 * C;
+      if ((rc = dev_alloc(p, &ws, static_cast<size_t>(K_pad) * Kts)) != TLXCV_OK) return rc;
+      TLX_CUDA(ctx, pack_conv_weights(d.filters, ws, K, K_pad, C, R, S, 1, kModeSlabDense, Kts, st));
+    }
+    std::string serr = conv3x3_slab_prepare(op.slab, ctx->sm_count, act_in, N, H, W, C, K, groups, ws, Kts, out_bf16, res_bf16);
     if (serr.empty()) {
       SlabParams& sp = op.slab.p;
-      sp.scale = op.scale, sp.shift = op.shift, sp.act = d.act1, sp.alpha = d.alpha1;
+      sp.scale = op.scale, sp.shift = op.shift, sp.act = d.act1, sp.alpha = d.alpha1, sp.act2 = d.act2, sp.alpha2 = d.alpha2;
       op.impl = kImplSlab;
-      set_info(op, "conv3x3_slab_n64", 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.slab.grid, op.slab.threads,
-               op.slab.smem, op.slab.block_n);
+      set_info(op, groups > 1 ? "conv3x3_slab_grouped" : (C == 32 ? "conv3x3_slab_c32" : "conv3x3_slab_n64"), 1,
+               flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.slab.grid, op.slab.threads, op.slab.smem, op.slab.block_n);
       return TLXCV_OK;
     }
   }
