@@ -355,6 +355,27 @@ conv3x3_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         cur_cb = it.cb;
       }
       const bool in_seg = q < valid_w && trow < T;
+      // copy-out plan of this thread for the item (at most 4 chunks of 16 B per step): staging offset, offset from the
+      // step's first output pixel, and the output row within the step; -1 = nothing
+      constexpr int kCopyIters = (kTileM * kChunks) / (kEpiWarpsB * 32);  // 4
+      uint32_t cp_smem[kCopyIters];
+      int cp_row[kCopyIters];
+      size_t cp_gl[kCopyIters];
+      {
+        const int per_row = valid_w * kChunks;
+#pragma unroll
+        for (int j = 0; j < kCopyIters; ++j) {
+          const int i = et + j * kEpiWarpsB * 32;
+          const int r = i / per_row, k = i - r * per_row;
+          const uint32_t w = static_cast<uint32_t>(k) / kChunks, cidx = static_cast<uint32_t>(k) % kChunks;
+          const uint32_t px = static_cast<uint32_t>(r * Ws) + w;
+          cp_row[j] = r < T ? r : 1 << 20;
+          cp_smem[j] = px * kOutBytes + ((cidx ^ (px & 7)) << 4);
+          cp_gl[j] = (static_cast<size_t>(r) * p.W + w) * pix_stride + cidx * 16;
+        }
+      }
+      uint8_t* const item_out = reinterpret_cast<uint8_t*>(p.out) +
+                                (static_cast<size_t>(it.n) * p.H * p.W + it.x0) * pix_stride + (it.cb * kBlockN) * 2;
       for (int m = 0; m < it.steps; ++m) {
         const int prow0 = it.p0 + m * T;
         const int n_rows = min(T, it.p1 - prow0);
@@ -420,19 +441,16 @@ conv3x3_slab_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         if (!(p.ablate & 8)) {
           // consecutive threads -> consecutive 16 B: the 8 chunks of a pixel are one 128-byte run, pixels of a row are
           // Cout*2 bytes apart (one contiguous run per row when the layer has a single channel block)
-          const int per_row = valid_w * kChunks;
-          for (int i = et; i < n_rows * per_row; i += kEpiWarpsB * 32) {
-            const int r = i / per_row, k = i - r * per_row;
-            const uint32_t w = static_cast<uint32_t>(k) / kChunks, cidx = static_cast<uint32_t>(k) % kChunks;
-            const uint32_t px = static_cast<uint32_t>(r * Ws) + w;
-            uint4 val;
-            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
-                         : "r"(sb + px * kOutBytes + ((cidx ^ (px & 7)) << 4)));
-            uint8_t* gdst = reinterpret_cast<uint8_t*>(p.out) +
-                            ((static_cast<size_t>(it.n) * p.H + prow0 + r) * p.W + it.x0 + w) * pix_stride +
-                            (it.cb * kBlockN) * 2 + cidx * 16;
-            *reinterpret_cast<uint4*>(gdst) = val;
+          uint8_t* const step_out = item_out + static_cast<size_t>(prow0) * p.W * pix_stride;
+#pragma unroll
+          for (int j = 0; j < kCopyIters; ++j) {
+            if (cp_row[j] < n_rows) {
+              uint4 val;
+              asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                           : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                           : "r"(sb + cp_smem[j]));
+              *reinterpret_cast<uint4*>(step_out + cp_gl[j]) = val;
+            }
           }
         }
         sbuf ^= 1;

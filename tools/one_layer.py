@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--res", action="store_true")
     ap.add_argument("--act", default="relu")
     ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--act-first", action="store_true", help="y = act(bn(conv(x))) + r (DarkNet) instead of act(bn(conv(x)) + r)")
     a = ap.parse_args()
     acts = {"none": None, "relu": nn.ReLU, "relu6": nn.ReLU6, "leaky": lambda: nn.LeakyReLU(0.1)}
 
@@ -44,6 +45,9 @@ def main():
 
         def forward(self, x, r=None):
             y = self.bn(self.conv(self.pre(x)))
+            if a.act_first:
+                y = self.act(y) if self.act is not None else y
+                return y + r if r is not None else y
             if r is not None:
                 y = y + r
             return self.act(y) if self.act is not None else y
