@@ -140,7 +140,9 @@ template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool D
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
   static_assert(!DUAL || (BLOCK_N == 128 && !RES && !F32), "dual accumulators: 128-wide bf16 tiles without a residual");
   constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
-  const int kCpw = a.cpw;  // chunks per warp per tile: the tile's BLOCK_N / 32 chunks over epi_warps / 4 column groups
+  // chunks per warp per tile: the tile's BLOCK_N / 32 chunks over epi_warps / 4 column groups (compile-time for the
+  // 8-warp build; a.cpw when kEpiWarps is raised for experiments)
+  const int kCpw = kEpiWarps == 8 ? (BLOCK_N / 32) / 2 : a.cpw;
   const int c_first = cgroup * kCpw;
   const int swz_own = (lane >> 1) & 3;
   const uint32_t own_row = a.ring + lane * 64;
