@@ -126,6 +126,11 @@ LAYERS = {
     "slab_3x3_c64_many_bands": (dict(n=160, cin=64, hw=10, cout=64, k=3, stride=1, pad=1, act="relu"), "conv3x3_slab"),
     "im2col_3x3_s2": (dict(n=2, cin=128, hw=28, cout=128, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_im2col"),
     "im2col_3x3_7x7_images_wrap": (dict(n=5, cin=256, hw=7, cout=256, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col"),
+    "pair_1x1_k1024_odd_tiles": (dict(n=3, cin=1024, hw=14, cout=256, k=1, stride=1, pad=0, act="relu"), "conv_tcgen05_tiled_n256_2sm"),
+    "pair_1x1_k512_residual_relu_two_n_tiles": (dict(n=2, cin=512, hw=14, cout=512, k=1, stride=1, pad=0, res=True, act2="relu"),
+                                                "conv_tcgen05_tiled_n256_2sm"),
+    "pair_3x3_s2_c256_leaky": (dict(n=3, cin=256, hw=19, cout=512, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col_n256_2sm"),
+    "pair_3x3_c256_14x14_bs9": (dict(n=9, cin=256, hw=14, cout=256, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col_n256_2sm"),
     "im2col_1x1_s2_downsample": (dict(n=2, cin=256, hw=14, cout=512, k=1, stride=2, pad=0), "conv_tcgen05_im2col"),
     "im2col_3x3_c32_leaky": (dict(n=2, cin=32, hw=20, cout=64, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col"),
     "im2col_leaky_then_residual": (dict(n=2, cin=64, hw=10, cout=128, k=3, stride=1, pad=1, act="leaky", res=True),
@@ -161,7 +166,14 @@ LAYERS = {
 @pytest.mark.parametrize("name", sorted(LAYERS))
 def test_fused_layer_matches_reference_math(name):
     kw, kernel = LAYERS[name]
-    err, tol, kernels, finite = _layer_case(**kw, seed=sum(map(ord, name)))
+    if kernel.endswith("_2sm"):      # small test shapes: force the CTA-pair (cta_group::2) variant the planner keeps for big maps
+        os.environ["TLXCV_DEBUG_2SM"] = "1"
+        os.environ["TLXCV_FORCE_BLOCK_N"] = "256"
+    try:
+        err, tol, kernels, finite = _layer_case(**kw, seed=sum(map(ord, name)))
+    finally:
+        os.environ.pop("TLXCV_DEBUG_2SM", None)
+        os.environ.pop("TLXCV_FORCE_BLOCK_N", None)
     assert any(k.startswith(kernel) for k in kernels), kernels
     assert finite and err <= tol, f"{name}: max err {err:.4g} > {tol:.4g}"
 

@@ -48,17 +48,19 @@ template <int BLOCK_N>
 struct Cfg {
   static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStageBytes2 = kABytes + kBBytes / 2;  // cta_group::2: each CTA of the pair stages half of B
   // smem layout: [stages x (A | B)] [8 warps x ring x 2 KB] [scale cache] [barriers]; the ring depth
   // and therefore the stage count are chosen per layer (deep ring for residual / HBM-bound layers,
   // more operand stages for MMA-bound ones)
   static constexpr int staging_bytes(int ring, int epi_warps) { return epi_warps * ring * 2048; }
-  static constexpr int stages_for(int ring, int sc_bufs, int epi_warps) {
-    const int n = (kSmemLimit - staging_bytes(ring, epi_warps) - sc_bufs * kScaleBufBytes - kBarrierBytes) / kStageBytes;
+  static constexpr int stages_for(int ring, int sc_bufs, int epi_warps, bool two = false) {
+    const int n = (kSmemLimit - staging_bytes(ring, epi_warps) - sc_bufs * kScaleBufBytes - kBarrierBytes) /
+                  (two ? kStageBytes2 : kStageBytes);
     return n > kMaxStages ? kMaxStages : n;
   }
-  static constexpr int smem_bytes(int ring, int sc_bufs, int epi_warps) {
-    return stages_for(ring, sc_bufs, epi_warps) * kStageBytes + staging_bytes(ring, epi_warps) + sc_bufs * kScaleBufBytes +
-           kBarrierBytes;
+  static constexpr int smem_bytes(int ring, int sc_bufs, int epi_warps, bool two = false) {
+    return stages_for(ring, sc_bufs, epi_warps, two) * (two ? kStageBytes2 : kStageBytes) + staging_bytes(ring, epi_warps) +
+           sc_bufs * kScaleBufBytes + kBarrierBytes;
   }
 };
 
@@ -70,6 +72,65 @@ __device__ __forceinline__ void trace_c(unsigned long long* buf, int role, int& 
     asm volatile("mov.u64 %0, %%clock64;" : "=l"(t));
     buf[role * kTraceLenC + idx++] = t;
   }
+}
+
+// ---- cta_group::2 (CTA pair) helpers --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t addr, uint32_t rank) {
+  uint32_t out;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(out) : "r"(addr), "r"(rank));
+  return out;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA loads of a CTA pair: the bytes land in THIS CTA's shared memory, the transaction count goes to `bar`, a
+// shared::cluster address that may belong to the peer (the leader's full barrier)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(uint32_t dst, const CUtensorMap* m, uint32_t bar, int c, int w, int h,
+                                                       int n, uint16_t off_w, uint16_t off_h) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on the barrier at this offset in BOTH CTAs of the pair when all MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(static_cast<uint16_t>(3))
+               : "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "n"(kCols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+template <uint32_t kCols>
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols) : "memory");
 }
 
 struct PipeState {
@@ -107,6 +168,8 @@ struct EpiArgs {
   const float* scale2;  // DUAL: folded BN of the second accumulator
   const float* shift2;
   int cpw;
+  int two, rank;              // cta_group::2: tiles are PAIRS of M tiles, this CTA owns M tile 2 * pair + rank
+  uint32_t tmem_empty_remote; // cta_group::2: shared::cluster address of the LEADER's tmem_empty barriers
   const float* scale;
   const float* shift;
   float* out_f32;
@@ -151,7 +214,8 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   int pf_tile = a.first_tile, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0;
   uint32_t pf = 0;
   auto pf_place = [&]() {
-    const int m_tile = pf_tile / a.n_tiles, n_tile = pf_tile - m_tile * a.n_tiles;
+    const int m_pair = pf_tile / a.n_tiles, n_tile = pf_tile - m_pair * a.n_tiles;
+    const int m_tile = a.two ? 2 * m_pair + a.rank : m_pair;
     pf_m0 = m_tile * kBlockM + lg * 32;
     pf_n0 = n_tile * BLOCK_N;
     pf_nmy = min(min(kCpw, BLOCK_N / 32 - c_first), max(0, (a.Cout - (pf_n0 + c_first * 32) + 31) / 32));
@@ -181,7 +245,8 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   int tr = 0;
   const bool tracer = a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;  // warp 2
   for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
-    const int m_tile = tile / a.n_tiles, n_tile = tile - m_tile * a.n_tiles;
+    const int m_pair = tile / a.n_tiles, n_tile = tile - m_pair * a.n_tiles;
+    const int m_tile = a.two ? 2 * m_pair + a.rank : m_pair;
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = max(0, min(min(kCpw, BLOCK_N / 32 - c_first), (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
@@ -214,7 +279,13 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       }
       __syncwarp();
     }
-    if (n_my == 0 && lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);  // nothing to read: release at once
+    auto release_acc = [&]() {  // one arrival per epilogue warp; a CTA pair counts on the leader's barrier
+      if (a.two)
+        mbar_arrive_cluster(a.tmem_empty_remote + acc * 8);
+      else
+        mbar_arrive(a.tmem_empty_bar + acc * 8);
+    };
+    if (n_my == 0 && lane == 0) release_acc();  // nothing to read: release at once
 #pragma unroll 1
     for (int ci = 0; ci < n_my; ++ci, ++it) {
       const int chunk = c_first + ci;
@@ -281,7 +352,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         // measurable cost)
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(a.tmem_empty_bar + acc * 8);
+        if (lane == 0) release_acc();
       }
       if (F32) {
         const int gr = m0 + lane;
@@ -343,7 +414,12 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
 //                            either as a plain [M][C2] matrix (s = 1) or through im2col-mode TMA (s = 2)),
 // combined by the epilogue.  It replaces `out = relu(bn3(conv3(x2)) + bn_d(conv_d(x)))` of a ResNet / ResNeXt
 // stage's first block (classification/resnet.py:142-156, :246-261) without the downsample map ever reaching HBM.
-template <int BLOCK_N, int MODE, bool DUAL = false>
+// TWO (BLOCK_N = 256): the kernel runs as CTA PAIRS (cluster of 2, `tcgen05.mma.cta_group::2`): a pair owns a
+// 256-pixel x 256-channel tile, each CTA stages its own 128 pixel rows of A and HALF of the weight tile, the leader
+// issues 256x256x16 MMAs that read both CTAs' shared memory and write both CTAs' TMEM, every CTA drains its own 128
+// accumulator rows.  Per CTA and K block that is 16 KB + 16 KB from L2 instead of 16 KB + 32 KB: the MMA-bound
+// layers are limited by exactly that L2 -> SM operand traffic.
+template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
 __global__ void __launch_bounds__(MODE == kModeGatherC4 ? kThreadsGather : kThreadsBase, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapOut, const __grid_constant__ CUtensorMap tmapRes,
@@ -351,8 +427,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                     const ConvKernelParams p) {
   using C = Cfg<BLOCK_N>;
   static_assert(!DUAL || (BLOCK_N == 128 && MODE == kModeTiled), "dual accumulators: 128-wide tiles over a tiled first operand");
+  static_assert(!TWO || (BLOCK_N == 256 && !DUAL && MODE != kModeGatherC4), "CTA pairs: 256-wide plain tiles");
   constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
   constexpr int kTmemColsK = 2 * kAccCols;
+  constexpr int kStageB = TWO ? C::kStageBytes2 : C::kStageBytes;
+  const uint32_t rank = TWO ? cluster_ctarank() : 0;   // 0 = leader of the pair
   // SWIZZLE_128B operand tiles need 1024-byte alignment; no pointer casts through integers here, so
   // that the compiler keeps the shared address space (LDS/STS instead of generic LD/ST)
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -360,7 +439,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   const int n_stages = p.stages, ring = p.ring;
   const int epi_warps = p.epi_warps;
   const int staging_bytes = epi_warps * ring * 2048;
-  uint8_t* staging = smem + n_stages * C::kStageBytes;
+  uint8_t* staging = smem + n_stages * kStageB;
   float* sc_cache = reinterpret_cast<float*>(staging + staging_bytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + p.sc_bufs * kScaleBufBytes);
   uint64_t* full_bar = bars;                       // [kStages]  operands landed
@@ -372,7 +451,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_tiles = p.m_tiles * p.n_tiles;
+  // work units: tiles, or (pair of M tiles) x N tile for CTA pairs; unit u belongs to worker u mod n_workers
+  const int num_tiles = TWO ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int worker = TWO ? blockIdx.x >> 1 : blockIdx.x, n_workers = TWO ? gridDim.x >> 1 : gridDim.x;
 
   if (warp == 1 && lane == 0) {
     if (MODE != kModeGatherC4) tma_prefetch_desc(&tmapA);
@@ -388,13 +469,18 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&tmem_full_bar[i]), 1);
-      mbar_init(smem_u32(&tmem_empty_bar[i]), epi_warps);  // one arrival per epilogue warp
+      mbar_init(smem_u32(&tmem_empty_bar[i]), TWO ? 2 * epi_warps : epi_warps);  // one arrival per epilogue warp (of the pair)
     }
     for (int i = 0; i < kEpiWarps * kMaxRing; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
     if (!p.out_f32 && p.residual != nullptr) tma_prefetch_desc(&tmapRes);
     fence_barrier_init();
   }
-  if (warp == 0) tmem_alloc<kTmemColsK>(smem_u32(tmem_ptr_smem));
+  if (warp == 0) {
+    if (TWO)
+      tmem_alloc_2sm<kTmemColsK>(smem_u32(tmem_ptr_smem));
+    else
+      tmem_alloc<kTmemColsK>(smem_u32(tmem_ptr_smem));
+  }
   const bool sc_cached = p.n_tiles == 1 && !DUAL;  // one N tile: scale/shift never change, keep them in smem
   if (sc_cached && warp >= 2 && warp < 2 + epi_warps) {
     for (int i = threadIdx.x - 64; i < BLOCK_N; i += epi_warps * 32) {
@@ -403,7 +489,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (TWO)
+    cluster_sync_all();  // both CTAs' barriers are initialised before any remote arrival / multicast commit
+  else
+    __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr_smem;
   pdl_wait();               // the previous kernel's activations are complete and visible from here on
@@ -415,9 +504,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       PipeState ps;
       const int PQ = p.P * p.Q;
       int tr = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += n_workers) {
         trace_c(p.trace, 0, tr);  // [2k] tile start
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        const int m_pair = tile / p.n_tiles, n_tile = tile - m_pair * p.n_tiles;
+        const int m_tile = TWO ? 2 * m_pair + static_cast<int>(rank) : m_pair;  // a pair's second tile may lie past M: zero-filled
         const int m0 = m_tile * kBlockM, n0 = n_tile * BLOCK_N;
         int img = 0, base_h = 0, base_w = 0;
         if (MODE == kModeIm2col || (DUAL && p.a2_im2col)) {
@@ -433,7 +523,25 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
-          const uint32_t a_dst = smem_u32(smem + ps.stage * C::kStageBytes);
+          const uint32_t a_dst = smem_u32(smem + ps.stage * kStageB);
+          if constexpr (TWO) {
+            // both CTAs' bytes are counted on the LEADER's full barrier, which alone is armed (for both halves)
+            const uint32_t lbar = mapa_u32(bar, 0);
+            if (rank == 0) mbar_arrive_expect_tx(bar, 2 * kStageB);
+            if (MODE == kModeTiled) {
+              tma_load_2d_2sm(a_dst, &tmapA, lbar, kb * kBlockK, m0);
+            } else {
+              tma_load_im2col_4d_2sm(a_dst, &tmapA, lbar, c_base + cb * kBlockK, base_w, base_h, img,
+                                     static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+              if (++cb == p.kb_per_tap) {
+                cb = 0;
+                if (++sx == p.S) sx = 0, ++r;
+              }
+            }
+            tma_load_2d_2sm(a_dst + kABytes, &tmapB, lbar, kb * kBlockK, n0 + static_cast<int>(rank) * (BLOCK_N / 2));
+            ps.advance(n_stages);
+            continue;
+          }
           mbar_arrive_expect_tx(bar, MODE == kModeGatherC4 ? C::kBBytes : C::kStageBytes);
           if (DUAL && kb >= p.num_kb1) {
             // second GEMM: 1x1 filter, so the K block is just a 64-channel slice of the (strided) input pixels
@@ -464,12 +572,12 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (one thread) =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N);
+    if (lane == 0 && rank == 0) {  // in a CTA pair only the leader issues
+      constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * kBlockM : kBlockM, BLOCK_N);
       PipeState ps;
       uint32_t acc = 0, acc_phase = 0;
       int tr = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int tile = worker; tile < num_tiles; tile += n_workers) {
         trace_c(p.trace, 1, tr);  // [4k] tile start
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
@@ -482,18 +590,30 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           mbar_wait(smem_u32(&full_bar[ps.stage]), ps.phase);
           tcgen05_fence_after();
           if (kb == 0) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
-          const uint32_t a_addr = smem_u32(smem + ps.stage * C::kStageBytes);
+          const uint32_t a_addr = smem_u32(smem + ps.stage * kStageB);
           const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
           const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kABytes);
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            if (!(p.ablate & 4)) umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kbl | k) != 0);
+            if (p.ablate & 4) continue;
+            if (TWO)
+              umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kbl | k) != 0);
+            else
+              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kbl | k) != 0);
           }
-          umma_commit(smem_u32(&empty_bar[ps.stage]));  // frees the smem stage when these MMAs retire
+          // frees the smem stage (of both CTAs of a pair) when these MMAs retire
+          if (TWO)
+            umma_commit_2sm(smem_u32(&empty_bar[ps.stage]));
+          else
+            umma_commit(smem_u32(&empty_bar[ps.stage]));
           ps.advance(n_stages);
         }
-        umma_commit(smem_u32(&tmem_full_bar[acc]));  // accumulator ready for the epilogue
+        // accumulator ready for the epilogue (of both CTAs of a pair)
+        if (TWO)
+          umma_commit_2sm(smem_u32(&tmem_full_bar[acc]));
+        else
+          umma_commit(smem_u32(&tmem_full_bar[acc]));
         trace_c(p.trace, 1, tr);  // [4k+3] all MMAs of the tile issued
         if (++acc == 2) {
           acc = 0;
@@ -518,7 +638,9 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.out_f32 = reinterpret_cast<float*>(p.out);
     a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
     a.M = p.M, a.Cout = p.Cout, a.n_tiles = p.n_tiles, a.num_tiles = num_tiles;
-    a.first_tile = blockIdx.x, a.tile_stride = gridDim.x;
+    a.first_tile = worker, a.tile_stride = n_workers;
+    a.two = TWO ? 1 : 0, a.rank = static_cast<int>(rank);
+    a.tmem_empty_remote = TWO ? mapa_u32(smem_u32(tmem_empty_bar), 0) : 0;
     a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
     a.ablate = p.ablate;
     a.trace = p.trace;
@@ -618,10 +740,16 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (TWO)
+    cluster_sync_all();  // the peer's shared memory and TMEM stay valid until both CTAs are done
+  else
+    __syncthreads();
   if (warp == 0) {
     tcgen05_fence_after();
-    tmem_dealloc<kTmemColsK>(tmem_base);
+    if (TWO)
+      tmem_dealloc_2sm<kTmemColsK>(tmem_base);
+    else
+      tmem_dealloc<kTmemColsK>(tmem_base);
   }
 }
 
@@ -702,7 +830,21 @@ inline int& conv_launch_counter() {
   return n;
 }
 
-template <int BLOCK_N, int MODE, bool DUAL = false>
+// cluster of 2 + programmatic dependent launch
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pair(void (*kernel)(KArgs...), int grid, int block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid), cfg.blockDim = dim3(block), cfg.dynamicSmemBytes = smem, cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2, attr[0].val.clusterDim.y = 1, attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr, cfg.numAttrs = 2;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
   // debugging: dump CTA 0's timeline of conv launch number TLXCV_DEBUG_TRACE_CONV_INDEX (default: every launch, so the
   // file holds the last one)
@@ -716,7 +858,11 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
     cudaMemsetAsync(dbuf, 0, 3 * kTraceLenC * sizeof(unsigned long long), st);
     ConvKernelParams p = L.p;
     p.trace = dbuf;
-    conv_tcgen05_kernel<BLOCK_N, MODE, DUAL><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.tmapA2, L.tmapB2, p);
+    if (TWO)
+      launch_pair(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut, L.tmapRes,
+                  L.tmapA2, L.tmapB2, p);
+    else
+      conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.tmapA2, L.tmapB2, p);
     cudaStreamSynchronize(st);
     std::vector<unsigned long long> h(3 * kTraceLenC);
     cudaMemcpy(h.data(), dbuf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -726,21 +872,26 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
     }
     return cudaGetLastError();
   }
-  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
+  if (TWO)
+    return launch_pair(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
+                       L.tmapRes, L.tmapA2, L.tmapB2, L.p);
+  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
                     L.tmapRes, L.tmapA2, L.tmapB2, L.p);
 }
 
-template <int BLOCK_N, int MODE, bool DUAL = false>
+template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
 cudaError_t set_attr_t() {
-  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kSmemLimit);
 }
 
-int smem_for(int block_n, int ring, int sc_bufs, int ew) {
+int smem_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
+  if (two) return Cfg<256>::smem_bytes(ring, sc_bufs, ew, true);
   return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs, ew)
                         : (block_n == 128 ? Cfg<128>::smem_bytes(ring, sc_bufs, ew) : Cfg<64>::smem_bytes(ring, sc_bufs, ew));
 }
-int stages_for(int block_n, int ring, int sc_bufs, int ew) {
+int stages_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
+  if (two) return Cfg<256>::stages_for(ring, sc_bufs, ew, true);
   return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs, ew)
                         : (block_n == 128 ? Cfg<128>::stages_for(ring, sc_bufs, ew) : Cfg<64>::stages_for(ring, sc_bufs, ew));
 }
@@ -751,7 +902,7 @@ int stages_for(int block_n, int ring, int sc_bufs, int ew) {
 // faster: ResNet-50 bs256 3.67 ms against 3.51 ms - the per-SM epilogue rate is set by shared-memory traffic (staging
 // stores, TMA store reads, scale/shift broadcasts next to the MMA operand reads) and the per-chunk proxy fence, not by
 // the number of warps issuing.
-void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_bf16) {
+void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_bf16, bool two = false) {
   static const int force = getenv("TLXCV_DEBUG_EPI_WARPS") ? atoi(getenv("TLXCV_DEBUG_EPI_WARPS")) : 0;
   const bool light = p.num_kb <= 8;
   p.epi_warps = 8;
@@ -762,9 +913,9 @@ void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_b
   if (!out_bf16) p.ring = 2;
   // scale/shift: one smem buffer filled once (single N tile); two buffers refreshed per tile by the epilogue
   // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
-  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps) == stages_for(block_n, p.ring, 1, p.epi_warps)) ? 2 : 1;
+  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps, two) == stages_for(block_n, p.ring, 1, p.epi_warps, two)) ? 2 : 1;
   if (const char* e = getenv("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
-  p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps);
+  p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
 }
 
 }  // namespace
@@ -794,6 +945,8 @@ cudaError_t tc_conv_set_attributes() {
   TLXCV_SET(64, kModeGatherC4) TLXCV_SET(128, kModeGatherC4)
 #undef TLXCV_SET
   if ((e = set_attr_t<128, kModeTiled, true>()) != cudaSuccess) return e;
+  if ((e = set_attr_t<256, kModeTiled, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr_t<256, kModeIm2col, false, true>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -864,14 +1017,22 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // residual layers and short-K (HBM / epilogue bound) layers get the deep store ring; long-K
   // (MMA bound) layers trade it for one more operand stage
   if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only: results are wrong
-  choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr);
-  L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps);
-  const long long tiles = static_cast<long long>(p.m_tiles) * p.n_tiles;
-  L.grid = static_cast<int>(std::min<long long>(tiles, sm_count));
+  // CTA pairs (cta_group::2) for the 256-wide layers with enough K per tile to be bound by MMA / L2 operand traffic
+  // rather than by the epilogue; TLXCV_DEBUG_2SM=0/1 forces it off / on where legal
+  // (measured on B200, bs256: 14x14 maps 1024->256 35.8 -> 33.8 us, 512->1024 58.4 -> 54.3 us; 7x7 maps with their 98
+  //  M tiles lose 3-5 %: pairs halve the number of schedulable units)
+  bool two = block_n == 256 && mode != kModeGatherC4 && out_bf16 != nullptr && p.num_kb >= 8 && p.m_tiles >= 256;
+  if (const char* e = getenv("TLXCV_DEBUG_2SM"))
+    two = atoi(e) != 0 && block_n == 256 && mode != kModeGatherC4 && out_bf16 != nullptr && p.m_tiles >= 2;
+  L.two = two ? 1 : 0;
+  choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two);
+  L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
+  const long long tiles = two ? static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles : static_cast<long long>(p.m_tiles) * p.n_tiles;
+  L.grid = two ? 2 * static_cast<int>(std::min<long long>(tiles, sm_count / 2)) : static_cast<int>(std::min<long long>(tiles, sm_count));
 
   // B: packed weights [Cout_pad][Ktot], K-major; Cout_pad is a multiple of 256 rows so any tile box is in bounds
   const int cout_pad = ((Cout + 255) / 256) * 256;
-  err = encode_2d(&L.tmapB, packed_w, Ktot, cout_pad, static_cast<uint64_t>(Ktot) * 2, kBlockK, block_n);
+  err = encode_2d(&L.tmapB, packed_w, Ktot, cout_pad, static_cast<uint64_t>(Ktot) * 2, kBlockK, L.two ? block_n / 2 : block_n);
   if (!err.empty()) return err;
   if (mode == kModeTiled) {
     err = encode_2d(&L.tmapA, act_in, Cin, p.M, static_cast<uint64_t>(Cin_storage) * 2, kBlockK, kBlockM);
@@ -948,6 +1109,7 @@ std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloa
 
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t st) {
   if (L.dual) return launch_t<128, kModeTiled, true>(L, st);
+  if (L.two) return L.mode == kModeTiled ? launch_t<256, kModeTiled, false, true>(L, st) : launch_t<256, kModeIm2col, false, true>(L, st);
 #define TLXCV_CASE(BN, MD) \
   if (L.block_n == BN && L.mode == MD) return launch_t<BN, MD>(L, st);
   TLXCV_CASE(64, kModeTiled) TLXCV_CASE(128, kModeTiled) TLXCV_CASE(256, kModeTiled)

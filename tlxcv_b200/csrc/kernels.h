@@ -59,6 +59,7 @@ struct TcConvLaunch {
   CUtensorMap tmapA, tmapB, tmapOut, tmapRes, tmapA2, tmapB2;
   ConvKernelParams p;
   int mode, block_n, grid, threads, smem, dual;
+  int two;  // launched as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2)
 };
 
 // Encodes the TMA descriptors and picks tile shape; returns an empty string or an error message.

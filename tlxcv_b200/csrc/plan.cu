@@ -401,7 +401,8 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   op.impl = kImplTcConv;
   char name[48];
   static const char* mnames[] = {"tiled", "im2col", "gatherc4"};
-  snprintf(name, sizeof name, "conv_tcgen05_%s_n%d%s", mnames[op.tc.mode], op.tc.block_n, groups > 1 ? "_grouped" : "");
+  snprintf(name, sizeof name, "conv_tcgen05_%s_n%d%s%s", mnames[op.tc.mode], op.tc.block_n, groups > 1 ? "_grouped" : "",
+           op.tc.two ? "_2sm" : "");
   // tensor-bound when arithmetic intensity exceeds the ridge (~248 FLOP/B on the measured peaks)
   set_info(op, name, 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.tc.grid, op.tc.threads, op.tc.smem, op.tc.block_n);
   return TLXCV_OK;
