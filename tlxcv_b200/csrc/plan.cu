@@ -329,7 +329,11 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
     set_info(op, "conv_direct_f32", 1, 1, flops, bytes, 0, 256, 0, 0);
     return TLXCV_OK;
   }
-  const bool depthwise = !is_linear && groups == C && K == C && groups > 1;
+  // depthwise layers the slab kernel covers (64-channel blocks, stride 1, wide maps) run on the tensor cores with
+  // diagonal weight taps: the CUDA-core kernel is bound by its instruction count (~40 per output)
+  const bool dw_on_slab = !is_linear && groups == C && K == C && groups > 1 && in.cs == C && d.in1 < 0 && !getenv("TLXCV_NO_DW_SLAB") &&
+                          conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups);
+  const bool depthwise = !is_linear && groups == C && K == C && groups > 1 && !dw_on_slab;
   if (depthwise) {
     if (dil != 1) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "depthwise conv: dilation must be 1");
     __nv_bfloat16* w = nullptr;
