@@ -167,6 +167,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line (NCCL prints its version at INFO)
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank)
