@@ -58,7 +58,7 @@ typedef enum {
   TLXCV_ERR_OOM = -5
 } tlxcv_status;
 
-typedef enum { TLXCV_F32 = 0, TLXCV_BF16 = 1, TLXCV_I64 = 2, TLXCV_ACT = 3 } tlxcv_dtype;
+typedef enum { TLXCV_F32 = 0, TLXCV_BF16 = 1, TLXCV_I64 = 2, TLXCV_ACT = 3, TLXCV_U8 = 4 } tlxcv_dtype;
 /* TLXCV_ACT: the plan's activation type — bf16 (TLXCV_PREC_BF16) or fp32 (TLXCV_PREC_F32_VALIDATE). */
 
 typedef enum { TLXCV_ROLE_INTERNAL = 0, TLXCV_ROLE_INPUT = 1, TLXCV_ROLE_OUTPUT = 2 } tlxcv_role;
@@ -71,7 +71,11 @@ typedef enum {
   TLXCV_OP_LINEAR = 4,       /* (N, F) x (F, K) + bias -> fp32 logits                              */
   TLXCV_OP_ADD_ACT = 5,      /* act2(in0 [+ in1]) — only for adds / activations no conv could absorb */
   TLXCV_OP_ARGMAX = 6,       /* (N, K) fp32 -> (N) int64                                           */
-  TLXCV_OP_EXPORT_NCHW = 7   /* internal NHWC activation -> external NCHW fp32                     */
+  TLXCV_OP_EXPORT_NCHW = 7,  /* internal NHWC activation -> external NCHW fp32                     */
+  TLXCV_OP_IMPORT_U8_NHWC = 8 /* external NHWC uint8 image batch (N, H, W, C<=4) -> internal activation
+                                 (x - mean[c]) / std[c]: the reference's host-side Normalize + ToTensor
+                                 (demo/image_classification/predict-resnet.py:50-54) fused into the layout
+                                 pass; bn_mean / bn_var carry device pointers to float mean[C] / std[C]      */
 } tlxcv_op_kind;
 
 typedef enum { TLXCV_ACT_NONE = 0, TLXCV_ACT_RELU = 1, TLXCV_ACT_RELU6 = 2, TLXCV_ACT_LEAKY = 3 } tlxcv_act;

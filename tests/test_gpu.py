@@ -463,6 +463,43 @@ def test_weight_update_rebuilds_the_plan():
     assert float((b - a - 1.0).abs().max()) < 1e-5
 
 
+def test_uint8_preprocessing_fused_into_the_input_kernel():
+    """uint8 NHWC batch -> (x - mean) / std -> stem, inside the plan: bit-identical logits to feeding
+    the host-normalised fp32 NCHW tensor, and within the bf16 bound of the oracle on that tensor."""
+    from oracle import restated
+    from tlxcv_b200 import models, vision
+    from tlxcv_b200.pipeline import HostPipeline
+    from tlxcv_b200.testing import seeded_state_dict
+
+    mean, std = (125.31, 122.95, 113.86), (62.99, 62.09, 66.70)
+    backbone = models.resnet18()
+    sd = seeded_state_dict(backbone.state_dict(), "resnet18")
+    backbone.load_state_dict(sd)
+    net = vision.Preprocessed(backbone, mean, std).cuda().set_eval()
+    g = torch.Generator().manual_seed(7)
+    u8 = torch.randint(0, 256, (6, 224, 224, 3), generator=g, dtype=torch.uint8)
+    x = ((u8.float() - torch.tensor(mean)) / torch.tensor(std)).permute(0, 3, 1, 2).contiguous()
+    y_u8 = net(u8.cuda()).cpu()
+    y_f32 = backbone(x.cuda()).cpu()
+    assert torch.equal(y_u8, y_f32)
+    ref = restated.forward("resnet18", sd, x)
+    assert float((y_u8 - ref).abs().max()) <= 1e-2
+    plan = next(iter(net.__dict__["_b200_plans"].values()))[0]
+    kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
+    assert kernels[0] == "import_u8_nhwc_padded" and kernels[1].startswith("stem_rowring")
+    # host pipeline with the 4x smaller uint8 batches
+    pipe = HostPipeline(net, tuple(u8.shape), dtype=torch.uint8)
+    out = torch.empty(6, 1000).pin_memory()
+    pipe.submit(u8.pin_memory(), out)
+    pipe.synchronize()
+    assert torch.equal(out, y_u8) and pipe.h2d_bytes == u8.numel()
+    # fp32 validation mode goes through the same op
+    from tlxcv_b200 import runtime
+    plan32, _, flat = runtime.get_plan(net, (u8.cuda(),), {}, precision=runtime.PREC_F32)
+    y32 = plan32.run(flat, graph=False)[0].cpu()
+    assert float((y32 - ref).abs().max()) <= 1e-4
+
+
 def test_host_pipeline_matches_device_path():
     from tlxcv_b200 import models
     from tlxcv_b200.pipeline import HostPipeline

@@ -175,3 +175,20 @@ def test_list_held_submodules_register_like_the_oracle():
     assert isinstance(m.darknet_conv_block_list, list) and len(m.darknet_conv_block_list) == 5
     rx = models.resnext50_32x4d()
     assert not any(k.startswith("block_list.") for k in rx.state_dict())   # already registered as bb_i_j
+
+
+def test_uint8_preprocessing_is_the_plan_input_op():
+    """vision.Preprocessed: the uint8 NHWC batch enters through import_u8_nhwc (Normalize + ToTensor fused into the
+    layout pass, demo/image_classification/predict-resnet.py:50-56), not through the fp32 NCHW import."""
+    from tlxcv_b200 import models, planner, vision
+
+    net = vision.Preprocessed(models.resnet18(), mean=(125.31, 122.95, 113.86), std=(62.99, 62.09, 66.70)).set_eval()
+    spec, _ = planner.plan_for_shapes(net, planner.Shape(4, 224, 224, 3, u8=True))
+    kinds = [k for k, _ in spec.summary()]
+    assert kinds[0] == "import_u8_nhwc" and "import_nchw" not in kinds
+    t_in = spec.tensors[spec.inputs[0]]
+    assert (t_in.n, t_in.h, t_in.w, t_in.c, t_in.dtype) == (4, 224, 224, 3, planner.DT_U8)
+    assert kinds[1] == "conv" and kinds[-1] == "linear"
+    import pytest
+    with pytest.raises(ValueError):
+        vision.NormalizeToTensor(mean=(1.0, 2.0), std=(1.0, 0.0))

@@ -137,6 +137,29 @@ __global__ void import_nchw_smallc_kernel(const float* __restrict__ src, T* __re
   }
 }
 
+// uint8 NHWC image batch -> normalised NHWC4 activations (optionally with zero pad columns): one thread per stored pixel
+template <typename T>
+__global__ void import_u8_nhwc_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, const float* __restrict__ mean,
+                                      const float* __restrict__ stdv, int C, int H, int W, int Wp, int pad_l, size_t total) {
+  pdl_wait();
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int wp = static_cast<int>(idx % Wp);
+  const size_t nh = idx / Wp;
+  const int w = wp - pad_l;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (w >= 0 && w < W) {
+    const uint8_t* s = src + (nh * W + w) * C;
+#pragma unroll
+    for (int c = 0; c < 4; ++c)
+      if (c < C) v[c] = __fdiv_rn(static_cast<float>(s[c]) - __ldg(mean + c), __ldg(stdv + c));
+  }
+  if constexpr (sizeof(T) == 2)
+    reinterpret_cast<uint2*>(dst)[idx] = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  else
+    reinterpret_cast<float4*>(dst)[idx] = make_float4(v[0], v[1], v[2], v[3]);
+}
+
 // general transpose [N][C][HW] fp32 -> [N][HW][C] T through a 32x32 smem tile
 template <typename T>
 __global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW) {
@@ -539,6 +562,17 @@ cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W,
     TLXCV_LAUNCH(import_nchw_tile_kernel<float>, grid, block, 0, st, src, static_cast<float*>(dst), C, static_cast<int>(HW));
   else
     TLXCV_LAUNCH(import_nchw_tile_kernel<__nv_bfloat16>, grid, block, 0, st, src, static_cast<__nv_bfloat16*>(dst), C, static_cast<int>(HW));
+  return cudaGetLastError();
+}
+
+cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, const float* stdv, int N, int C, int H, int W,
+                           int Wp, int pad_l, int is_f32, cudaStream_t st) {
+  if (C > 4) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * H * Wp;
+  if (is_f32)
+    TLXCV_LAUNCH(import_u8_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, src, static_cast<float*>(dst), mean, stdv, C, H, W, Wp, pad_l, total);
+  else
+    TLXCV_LAUNCH(import_u8_nhwc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, src, static_cast<__nv_bfloat16*>(dst), mean, stdv, C, H, W, Wp, pad_l, total);
   return cudaGetLastError();
 }
 

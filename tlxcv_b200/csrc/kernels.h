@@ -180,6 +180,9 @@ cudaError_t fold_bn(float* scale, float* shift, const float* gamma, const float*
 // ---- memory-bound kernels (T = __nv_bfloat16 or float, is_f32 selects) -------------------------
 cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W, int Cs, int is_f32, cudaStream_t st);
 cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W, int is_f32, cudaStream_t st);
+// NHWC uint8 (C <= 4) -> [N][H][Wp][4] activations, (x - mean[c]) / std[c]; Wp == W, pad_l == 0 for the dense layout
+cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, const float* stdv, int N, int C, int H, int W,
+                           int Wp, int pad_l, int is_f32, cudaStream_t st);
 cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad,
                          int is_f32, cudaStream_t st);
 cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st);

@@ -30,7 +30,7 @@ struct TensorRt {
 };
 
 enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
-                  kImplStem, kImplSlab, kImplNop };
+                  kImplStem, kImplSlab, kImplNop, kImplImportU8 };
 
 struct OpRt {
   tlxcv_op_desc d;
@@ -106,6 +106,7 @@ size_t dtype_size(const tlxcv_plan* p, int dt) {
     case TLXCV_F32: return 4;
     case TLXCV_BF16: return 2;
     case TLXCV_I64: return 8;
+    case TLXCV_U8: return 1;
     default: return p->esize;
   }
 }
@@ -432,6 +433,10 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
       else
         TLX_CUDA(ctx, import_nchw(static_cast<const float*>(pin), pout, in.d.n, in.d.c, in.d.h, in.d.w, out.cs, is_f32, st));
       break;
+    case kImplImportU8:
+      TLX_CUDA(ctx, import_u8_nhwc(static_cast<const uint8_t*>(pin), pout, d.bn_mean, d.bn_var, in.d.n, in.d.c, in.d.h, in.d.w,
+                                   out.wp > 0 ? out.wp : out.d.w, out.pad_l, is_f32, st));
+      break;
     case kImplStem:
       TLX_CUDA(ctx, stem_rowring_launch(op.stem, st));
       break;
@@ -602,7 +607,8 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         if (p->ops[k].d.out == d.in0) producer = k;
         if (p->ops[k].d.in0 == d.in0 || p->ops[k].d.in1 == d.in0) ++consumers;
       }
-      if (producer < 0 || p->ops[producer].d.kind != TLXCV_OP_IMPORT_NCHW || consumers != 1) continue;
+      if (producer < 0 || consumers != 1) continue;
+      if (p->ops[producer].d.kind != TLXCV_OP_IMPORT_NCHW && p->ops[producer].d.kind != TLXCV_OP_IMPORT_U8_NHWC) continue;
       StemGeometry g;
       if (!stem_rowring_geometry(g, in.d.c, p->tensors[d.out].d.c, in.d.h, in.d.w, d.r, d.s, d.stride, d.pad, d.dil, d.groups))
         continue;
@@ -722,6 +728,13 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         op.impl = kImplImport;
         set_info(op, o.wp > 0 ? "import_nchw_c4_padded" : (o.cs == 4 ? "import_nchw_c4" : "import_nchw_tile"), 1, 0, 0,
                  in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_IMPORT_U8_NHWC:
+        if (in.d.role != TLXCV_ROLE_INPUT || in.d.dtype != TLXCV_U8 || o.d.dtype != TLXCV_ACT || o.d.role != TLXCV_ROLE_INTERNAL ||
+            in.d.c > 4 || in.d.c != o.d.c || o.cs != 4 || !d.bn_mean || !d.bn_var)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: import_u8 expects external uint8 NHWC (C <= 4) + mean/std -> internal activation", i);
+        op.impl = kImplImportU8;
+        set_info(op, o.wp > 0 ? "import_u8_nhwc_padded" : "import_u8_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_EXPORT_NCHW:
         if (o.d.role != TLXCV_ROLE_OUTPUT || o.d.dtype != TLXCV_F32 || in.d.dtype != TLXCV_ACT || in.cs != in.d.c)

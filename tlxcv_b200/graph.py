@@ -86,8 +86,8 @@ class Graph:
         self.dtypes[tid] = dtype
         return t
 
-    def add_input(self, shape) -> SymTensor:
-        t = self.new_tensor(shape)
+    def add_input(self, shape, dtype="act") -> SymTensor:
+        t = self.new_tensor(shape, dtype)
         self.inputs.append(t.id)
         return t
 
@@ -111,6 +111,15 @@ class Graph:
         q = (w + 2 * pw - dw * (s - 1) - 1) // sw + 1
         attrs = dict(r=r, s=s, stride=(sh, sw), pad=(ph, pw), dil=(dh, dw), groups=g)
         return self._emit("conv", [x], (n, kout, p, q), attrs, layer)
+
+    def normalize_u8(self, x, layer) -> SymTensor:
+        """uint8 NHWC image batch -> logical (N, C, H, W) activation, (x - mean) / std per channel."""
+        if x.dtype != "u8" or len(x.shape) != 4:
+            raise TypeError(f"NormalizeToTensor {'.'.join(self._path)}: expects the uint8 (N, H, W, C) image batch")
+        n, h, w, c = x.shape
+        if c != len(layer.mean) or c > 4:
+            raise ValueError(f"NormalizeToTensor: {c} channels vs {len(layer.mean)} mean/std entries (at most 4)")
+        return self._emit("normalize_u8", [x], (n, c, h, w), {}, layer)
 
     def bn(self, x, layer) -> SymTensor:
         if x.shape[1] != layer.gamma.shape[0]:

@@ -14,13 +14,14 @@ from . import runtime
 
 
 class HostPipeline:
-    def __init__(self, module, batch_shape, depth: int = 2, device=None, gather=None):
-        """``batch_shape``: (N, C, H, W) of every submitted batch.  ``gather``: optional callable applied
-        to the device result before the D2H copy (e.g. ``tlxcv_b200.dist.gather_rows``)."""
+    def __init__(self, module, batch_shape, depth: int = 2, device=None, gather=None, dtype=torch.float32):
+        """``batch_shape``: (N, C, H, W) of every submitted fp32 batch, or (N, H, W, C) with ``dtype=torch.uint8`` for a
+        module that starts with ``vision.NormalizeToTensor``.  ``gather``: optional callable applied to the device
+        result before the D2H copy (e.g. ``tlxcv_b200.dist.gather_rows``)."""
         self.device = torch.device(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
         self.depth = depth
         self.gather = gather
-        self.dev_in = [torch.empty(batch_shape, dtype=torch.float32, device=self.device) for _ in range(depth)]
+        self.dev_in = [torch.empty(batch_shape, dtype=dtype, device=self.device) for _ in range(depth)]
         self.plan, self.structure, _ = runtime.get_plan(module, (self.dev_in[0],), {})
         if self.plan.n_in != 1 or self.plan.n_out != 1:
             raise NotImplementedError("HostPipeline handles single-input single-output modules")
@@ -30,7 +31,7 @@ class HostPipeline:
         self.ev_h2d = [torch.cuda.Event() for _ in range(depth)]
         self.ev_done = [torch.cuda.Event() for _ in range(depth)]
         self._i = 0
-        self.h2d_bytes = self.dev_in[0].numel() * 4
+        self.h2d_bytes = self.dev_in[0].numel() * self.dev_in[0].element_size()
 
     def submit(self, host_in: torch.Tensor, host_out: torch.Tensor):
         """Enqueue one batch: pinned ``host_in`` (N,C,H,W) fp32 -> device -> forward -> pinned ``host_out``."""

@@ -22,13 +22,14 @@ from typing import Any
 from . import graph as _g
 
 # op kinds / activations / dtypes: keep in sync with include/tlxcv_b200.h
-OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW = range(8)
+OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW, OP_IMPORT_U8 = range(9)
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY = range(4)
+DT_U8 = 4
 DT_F32, DT_BF16, DT_I64, DT_ACT = 0, 1, 2, 3          # DT_ACT: bf16 in the default mode, f32 in validation mode
 ROLE_INTERNAL, ROLE_INPUT, ROLE_OUTPUT = 0, 1, 2
 
 _ACT = {None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6, "leaky": ACT_LEAKY}
-OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw"]
+OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw", "import_u8_nhwc"]
 
 
 @dataclass
@@ -58,6 +59,7 @@ class OpSpec:
     act2: int = ACT_NONE
     alpha2: float = 0.0
     conv: Any = None      # GroupConv2d / Linear module (parameters are read at plan build)
+    norm: Any = None      # vision.NormalizeToTensor module (mean / std buffers)
     bn: Any = None        # BatchNorm module
     path: str = ""
 
@@ -78,6 +80,8 @@ class PlanSpec:
                 yield op.conv
             if op.bn is not None:
                 yield op.bn
+            if op.norm is not None:
+                yield op.norm
 
     def summary(self):
         return [(OP_NAMES[o.kind], o.path) for o in self.ops]
@@ -127,6 +131,14 @@ def lower(graph: _g.Graph) -> PlanSpec:
         shape = graph.shapes[tid]
         if len(shape) != 4:
             raise NotImplementedError(f"plan input must be (N, C, H, W), got {shape}")
+        if graph.dtypes[tid] == "u8":
+            # uint8 NHWC image batch: stays external until its (only) consumer, a vision.NormalizeToTensor node
+            n, h, w, c = shape
+            spec.tensors.append(TensorSpec(n, h, w, c, DT_U8, ROLE_INPUT))
+            spec.inputs.append(len(spec.tensors) - 1)
+            gid2plan[tid] = len(spec.tensors) - 1
+            produced_at[tid] = -1
+            continue
         ext = new_tensor(shape, DT_F32, ROLE_INPUT)
         spec.inputs.append(ext)
         inner = new_tensor(shape, DT_ACT)
@@ -171,6 +183,15 @@ def lower(graph: _g.Graph) -> PlanSpec:
             spec.ops.append(op)
             gid2plan[cur] = op.out
             produced_at[cur] = i
+            continue
+        if nd.op == "normalize_u8":
+            src = spec.tensors[ins[0]]
+            if src.dtype != DT_U8 or src.role != ROLE_INPUT:
+                raise NotImplementedError(f"{nd.path}: NormalizeToTensor takes the uint8 NHWC input batch of the forward")
+            out = new_tensor(graph.shapes[nd.out], DT_ACT)
+            spec.ops.append(OpSpec(OP_IMPORT_U8, ins[0], out, conv=None, path=nd.path, norm=nd.module))
+            gid2plan[nd.out] = out
+            produced_at[nd.out] = i
             continue
         if nd.op == "bn":
             raise NotImplementedError(f"{nd.path}: BatchNorm that does not follow a convolution is not on the hot path")
@@ -268,7 +289,8 @@ def trace(module, args, kwargs, is_tensor, shape_of):
         def to_sym(v):
             if is_tensor(v):
                 flat_inputs.append(v)
-                return g.add_input(shape_of(v))
+                is_u8 = str(getattr(v, "dtype", "")) == "torch.uint8" or getattr(v, "u8", False)
+                return g.add_input(shape_of(v), "u8" if is_u8 else "act")
             return v
 
         s_args = _map_structure(list(args), to_sym)
@@ -301,8 +323,9 @@ def fill_structure(structure, outputs):
 class Shape:
     """Stand-in for a real input tensor when planning on the CPU."""
 
-    def __init__(self, *dims):
+    def __init__(self, *dims, u8=False):
         self.dims = tuple(int(d) for d in dims)
+        self.u8 = bool(u8)      # a uint8 (N, H, W, C) image batch (vision.NormalizeToTensor input)
 
 
 def plan_for_shapes(module, *args, **kwargs):

@@ -146,6 +146,7 @@ class Plan:
             tens[i] = TensorDesc(t.n, t.h, t.w, t.c, t.dtype, t.role)
         ops = (OpDesc * len(spec.ops))()
         self._keep = []
+        self._norm_keep = []   # mean / std vectors of import_u8 ops: read by the kernel at every run
         for i, o in enumerate(spec.ops):
             d = OpDesc(kind=o.kind, in0=o.in0, in1=o.in1, out=o.out, r=o.r, s=o.s, stride=o.stride, pad=o.pad,
                        dil=o.dil, groups=o.groups, act1=o.act1, alpha1=o.alpha1, act2=o.act2, alpha2=o.alpha2,
@@ -155,6 +156,11 @@ class Plan:
                 b = _param(o.conv, "biases", device)
                 self._keep += [w, b]
                 d.filters, d.bias = _ptr(w), _ptr(b)
+            if getattr(o, "norm", None) is not None:
+                mean = o.norm.mean.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+                std = o.norm.std.detach().to(device=device, dtype=torch.float32).contiguous().clone()
+                self._norm_keep += [mean, std]
+                d.bn_mean, d.bn_var = _ptr(mean), _ptr(std)
             if o.bn is not None:
                 g, be = _param(o.bn, "gamma", device), _param(o.bn, "beta", device)
                 mu, var = _param(o.bn, "moving_mean", device), _param(o.bn, "moving_var", device)
@@ -191,6 +197,12 @@ class Plan:
             raise ValueError(f"plan takes {self.n_in} inputs")
         for x, ti in zip(inputs, self.spec.inputs):
             t = self.spec.tensors[ti]
+            if t.dtype == planner.DT_U8:
+                if tuple(x.shape) != (t.n, t.h, t.w, t.c) or x.dtype != torch.uint8 or not x.is_contiguous() \
+                        or x.device != self.device:
+                    raise B200RuntimeError(f"plan input must be contiguous uint8 NHWC {(t.n, t.h, t.w, t.c)} on "
+                                           f"{self.device}, got {x.dtype} {tuple(x.shape)} on {x.device}")
+                continue
             if tuple(x.shape) != (t.n, t.c, t.h, t.w) or x.dtype != torch.float32 or not x.is_contiguous() \
                     or x.device != self.device:
                 raise B200RuntimeError(f"plan input must be contiguous fp32 NCHW {(t.n, t.c, t.h, t.w)} on "
@@ -263,7 +275,7 @@ def param_fingerprint(spec):
     """(data_ptr, version) of every parameter a plan packed: a changed weight rebuilds the plan."""
     fp = []
     for m in spec.modules():
-        for p in m._parameters.values():
+        for p in list(m._parameters.values()) + list(m._buffers.values()):
             if p is not None:
                 fp.append((p.data_ptr(), p._version))
     return tuple(fp)
@@ -290,7 +302,7 @@ def get_plan(module, args, kwargs, precision=None):
         raise B200RuntimeError(
             f"tlxcv_b200 executes on a B200 only; got an input on {device} (there is no CPU fallback — move the "
             "model and the inputs to 'cuda')")
-    key = (tuple(tuple(t.shape) for t in probe), str(device), precision)
+    key = (tuple((tuple(t.shape), str(t.dtype)) for t in probe), str(device), precision)
     cache = module.__dict__.setdefault("_b200_plans", {})
     entry = cache.get(key)
     if entry is not None:
@@ -307,6 +319,7 @@ def get_plan(module, args, kwargs, precision=None):
 
 def run_module(module, args, kwargs):
     plan, structure, flat_inputs = get_plan(module, args, kwargs)
-    ins = [x if (x.dtype == torch.float32 and x.is_contiguous()) else x.float().contiguous() for x in flat_inputs]
+    ins = [x if (x.dtype in (torch.float32, torch.uint8) and x.is_contiguous()) else
+           (x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()) for x in flat_inputs]
     outs = plan.run(ins)
     return planner.fill_structure(structure, outs)
