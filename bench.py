@@ -246,6 +246,8 @@ def main():
     e2e_ms = torch.tensor([t0.elapsed_time(t1) / args.steps], device=device)
     if world > 1:
         tdist.all_reduce(e2e_ms, op=tdist.ReduceOp.MAX)
+    e2e_ok = bool(torch.equal(out_host[(args.steps - 1) % 2][rank * PER_GPU_BATCH:(rank + 1) * PER_GPU_BATCH],
+                              logits[0].cpu()))
     # ---- the same end-to-end call with uint8 NHWC host batches: Normalize + ToTensor run inside
     #      the plan's input kernel, so a step moves 38.5 MB instead of 154 MB across PCIe; informational, `e2e` above is
     #      the reference-facing fp32 NCHW call
@@ -269,8 +271,6 @@ def main():
     if world > 1:
         tdist.all_reduce(u8_ms, op=tdist.ReduceOp.MAX)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ok = bool(torch.equal(out_host[(args.steps - 1) % 2][rank * PER_GPU_BATCH:(rank + 1) * PER_GPU_BATCH],
-                              logits[0].cpu()))
 
     # ---- roofline of the dominant kernel family (conv on tcgen05), measured live --------------
     roof = None
