@@ -427,7 +427,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
                     const ConvKernelParams p) {
   using C = Cfg<BLOCK_N>;
   static_assert(!DUAL || (BLOCK_N == 128 && MODE == kModeTiled), "dual accumulators: 128-wide tiles over a tiled first operand");
-  static_assert(!TWO || (BLOCK_N == 256 && !DUAL && MODE != kModeGatherC4), "CTA pairs: 256-wide plain tiles");
+  static_assert(!TWO || ((BLOCK_N == 256 || BLOCK_N == 128) && !DUAL && MODE != kModeGatherC4), "CTA pairs: 128/256-wide plain tiles");
   constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
   constexpr int kTmemColsK = 2 * kAccCols;
   constexpr int kStageB = TWO ? C::kStageBytes2 : C::kStageBytes;
@@ -886,12 +886,12 @@ cudaError_t set_attr_t() {
 }
 
 int smem_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
-  if (two) return Cfg<256>::smem_bytes(ring, sc_bufs, ew, true);
+  if (two) return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs, ew, true) : Cfg<128>::smem_bytes(ring, sc_bufs, ew, true);
   return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs, ew)
                         : (block_n == 128 ? Cfg<128>::smem_bytes(ring, sc_bufs, ew) : Cfg<64>::smem_bytes(ring, sc_bufs, ew));
 }
 int stages_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
-  if (two) return Cfg<256>::stages_for(ring, sc_bufs, ew, true);
+  if (two) return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs, ew, true) : Cfg<128>::stages_for(ring, sc_bufs, ew, true);
   return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs, ew)
                         : (block_n == 128 ? Cfg<128>::stages_for(ring, sc_bufs, ew) : Cfg<64>::stages_for(ring, sc_bufs, ew));
 }
@@ -947,6 +947,8 @@ cudaError_t tc_conv_set_attributes() {
   if ((e = set_attr_t<128, kModeTiled, true>()) != cudaSuccess) return e;
   if ((e = set_attr_t<256, kModeTiled, false, true>()) != cudaSuccess) return e;
   if ((e = set_attr_t<256, kModeIm2col, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr_t<128, kModeTiled, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr_t<128, kModeIm2col, false, true>()) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1021,9 +1023,9 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // rather than by the epilogue; TLXCV_DEBUG_2SM=0/1 forces it off / on where legal
   // (measured on B200, bs256: 14x14 maps 1024->256 35.8 -> 33.8 us, 512->1024 58.4 -> 54.3 us; 7x7 maps with their 98
   //  M tiles lose 3-5 %: pairs halve the number of schedulable units)
-  bool two = block_n == 256 && mode != kModeGatherC4 && out_bf16 != nullptr && p.num_kb >= 8 && p.m_tiles >= 256;
-  if (const char* e = getenv("TLXCV_DEBUG_2SM"))
-    two = atoi(e) != 0 && block_n == 256 && mode != kModeGatherC4 && out_bf16 != nullptr && p.m_tiles >= 2;
+  const bool pairable = (block_n == 256 || block_n == 128) && groups == 1 && mode != kModeGatherC4 && out_bf16 != nullptr;
+  bool two = pairable && block_n == 256 && p.num_kb >= 8 && p.m_tiles >= 256;  // 128-wide pairs measured: no gain
+  if (const char* e = getenv("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && p.m_tiles >= 2;
   L.two = two ? 1 : 0;
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two);
   L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
@@ -1109,7 +1111,9 @@ std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloa
 
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t st) {
   if (L.dual) return launch_t<128, kModeTiled, true>(L, st);
-  if (L.two) return L.mode == kModeTiled ? launch_t<256, kModeTiled, false, true>(L, st) : launch_t<256, kModeIm2col, false, true>(L, st);
+  if (L.two && L.block_n == 256)
+    return L.mode == kModeTiled ? launch_t<256, kModeTiled, false, true>(L, st) : launch_t<256, kModeIm2col, false, true>(L, st);
+  if (L.two) return L.mode == kModeTiled ? launch_t<128, kModeTiled, false, true>(L, st) : launch_t<128, kModeIm2col, false, true>(L, st);
 #define TLXCV_CASE(BN, MD) \
   if (L.block_n == BN && L.mode == MD) return launch_t<BN, MD>(L, st);
   TLXCV_CASE(64, kModeTiled) TLXCV_CASE(128, kModeTiled) TLXCV_CASE(256, kModeTiled)
