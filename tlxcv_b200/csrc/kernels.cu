@@ -197,6 +197,48 @@ __global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __rest
   }
 }
 
+// bf16 NHWC -> fp32 NCHW, 64 channels x 64 pixels per block: 16-byte loads along C, smem transpose, 16-byte (or,
+// when HW is not a multiple of 4, 4-byte) stores along the pixels of one channel plane
+template <bool VEC4>
+__global__ void __launch_bounds__(256) export_nchw_bf16_64_kernel(const __nv_bfloat16* __restrict__ src, float* __restrict__ dst,
+                                                                   int C, int HW) {
+  pdl_wait();
+  __shared__ float tile[64][65];  // [channel][pixel]
+  const int n = blockIdx.z, c0 = blockIdx.y * 64, p0 = blockIdx.x * 64;
+  const __nv_bfloat16* s = src + static_cast<size_t>(n) * HW * C;
+  float* d = dst + static_cast<size_t>(n) * C * HW;
+  const int t = threadIdx.x;
+  {
+    const int cg = t & 7, pr = t >> 3;  // 8 channel groups of 8, 32 pixel rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 2; ++pass) {
+      const int pl = pr + pass * 32, p = p0 + pl, c = c0 + cg * 8;
+      float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (p < HW && c < C) Vec8<__nv_bfloat16>::load(s + static_cast<size_t>(p) * C + c, v);  // C is a multiple of 8
+#pragma unroll
+      for (int j = 0; j < 8; ++j) tile[cg * 8 + j][pl] = v[j];
+    }
+  }
+  __syncthreads();
+  if (VEC4) {
+    const int pq = t & 15, cr = t >> 4;  // 16 pixel quads, 16 channel rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 4; ++pass) {
+      const int cl = cr + pass * 16, c = c0 + cl, p = p0 + pq * 4;
+      if (c < C && p < HW)  // HW % 4 == 0: a quad is entirely inside or outside
+        *reinterpret_cast<float4*>(d + static_cast<size_t>(c) * HW + p) =
+            make_float4(tile[cl][pq * 4], tile[cl][pq * 4 + 1], tile[cl][pq * 4 + 2], tile[cl][pq * 4 + 3]);
+    }
+  } else {
+    const int pl = t & 63, cr = t >> 6;  // 64 pixels, 4 channel rows per pass
+#pragma unroll
+    for (int pass = 0; pass < 16; ++pass) {
+      const int cl = cr + pass * 4, c = c0 + cl, p = p0 + pl;
+      if (c < C && p < HW) d[static_cast<size_t>(c) * HW + p] = tile[cl][pl];
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // pooling
 // ------------------------------------------------------------------------------------------------
@@ -579,10 +621,17 @@ cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, con
 cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W, int is_f32, cudaStream_t st) {
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
-  if (is_f32)
+  if (is_f32) {
     TLXCV_LAUNCH(export_nchw_tile_kernel<float>, grid, block, 0, st, static_cast<const float*>(src), dst, C, HW);
-  else
+  } else if (C % 8 == 0) {
+    dim3 grid64((HW + 63) / 64, (C + 63) / 64, N);
+    if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
+      TLXCV_LAUNCH(export_nchw_bf16_64_kernel<true>, grid64, 256, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
+    else
+      TLXCV_LAUNCH(export_nchw_bf16_64_kernel<false>, grid64, 256, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
+  } else {
     TLXCV_LAUNCH(export_nchw_tile_kernel<__nv_bfloat16>, grid, block, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
+  }
   return cudaGetLastError();
 }
 
