@@ -160,6 +160,33 @@ __global__ void import_u8_nhwc_kernel(const uint8_t* __restrict__ src, T* __rest
     reinterpret_cast<float4*>(dst)[idx] = make_float4(v[0], v[1], v[2], v[3]);
 }
 
+// RGB fast path: four stored pixels per thread = three aligned 4-byte loads (12 bytes) and two 16-byte stores;
+// needs C == 3 and W, pad_l, Wp multiples of 4 (no group of four straddles the image edge)
+__global__ void import_u8_rgb_x4_kernel(const uint8_t* __restrict__ src, uint4* __restrict__ dst, const float* __restrict__ mean,
+                                        const float* __restrict__ stdv, int H, int W, int Wp4, int pad_l, size_t total) {
+  pdl_wait();
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int wq = static_cast<int>(idx % Wp4);
+  const size_t nh = idx / Wp4;
+  const int w = wq * 4 - pad_l;
+  uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;
+  if (w >= 0 && w < W) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src + (nh * W + w) * 3);
+    const uint32_t b0 = __ldg(s), b1 = __ldg(s + 1), b2 = __ldg(s + 2);
+    const float m0 = __ldg(mean), m1 = __ldg(mean + 1), m2 = __ldg(mean + 2);
+    const float d0 = __ldg(stdv), d1 = __ldg(stdv + 1), d2 = __ldg(stdv + 2);
+    auto byte = [&](int k) { return static_cast<float>(((k < 4 ? b0 : (k < 8 ? b1 : b2)) >> (8 * (k & 3))) & 0xffu); };
+    auto px = [&](int j, uint32_t& lo, uint32_t& hi) {
+      lo = pack_bf16x2(__fdiv_rn(byte(3 * j) - m0, d0), __fdiv_rn(byte(3 * j + 1) - m1, d1));
+      hi = pack_bf16x2(__fdiv_rn(byte(3 * j + 2) - m2, d2), 0.0f);
+    };
+    px(0, o0.x, o0.y), px(1, o0.z, o0.w), px(2, o1.x, o1.y), px(3, o1.z, o1.w);
+  }
+  dst[idx * 2] = o0;
+  dst[idx * 2 + 1] = o1;
+}
+
 // general transpose [N][C][HW] fp32 -> [N][HW][C] T through a 32x32 smem tile
 template <typename T>
 __global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW) {
@@ -610,6 +637,12 @@ cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W,
 cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, const float* stdv, int N, int C, int H, int W,
                            int Wp, int pad_l, int is_f32, cudaStream_t st) {
   if (C > 4) return cudaErrorInvalidValue;
+  if (!is_f32 && C == 3 && W % 4 == 0 && pad_l % 4 == 0 && Wp % 4 == 0 && (reinterpret_cast<uintptr_t>(src) & 3) == 0) {
+    const size_t total4 = static_cast<size_t>(N) * H * (Wp / 4);
+    TLXCV_LAUNCH(import_u8_rgb_x4_kernel, blocks_for(total4), kThreads, 0, st, src, static_cast<uint4*>(dst), mean, stdv, H, W, Wp / 4,
+                 pad_l, total4);
+    return cudaGetLastError();
+  }
   const size_t total = static_cast<size_t>(N) * H * Wp;
   if (is_f32)
     TLXCV_LAUNCH(import_u8_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, src, static_cast<float*>(dst), mean, stdv, C, H, W, Wp, pad_l, total);
