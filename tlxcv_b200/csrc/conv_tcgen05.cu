@@ -158,6 +158,61 @@ __device__ __forceinline__ void act_inplace(float (&f)[N], int act, float alpha)
   }
 }
 
+// ---- packed fp32x2 / bf16x2 helpers of the epilogue (sm_100: fma/add/mul.f32x2 work on 64-bit register pairs) ----------
+__device__ __forceinline__ unsigned long long pack_u64(uint32_t lo, uint32_t hi) {
+  return static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
+}
+__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
+  unsigned long long d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ unsigned long long bf16x2_to_f32x2(uint32_t u) {  // low half -> first float
+  return pack_u64(u << 16, u & 0xffff0000u);
+}
+__device__ __forceinline__ uint32_t pack_pair_bf16(unsigned long long p) {
+  return pack_bf16x2(__uint_as_float(static_cast<uint32_t>(p)), __uint_as_float(static_cast<uint32_t>(p >> 32)));
+}
+__device__ __forceinline__ ulonglong2 ldg_u64x2(const ulonglong2* p) {
+  ulonglong2 r;
+  asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
+  return r;
+}
+// activation of an fp32 pair.  LeakyReLU is max(v, alpha * v): exact for 0 <= alpha <= 1, which the planner enforces.
+template <int ACT>
+__device__ __forceinline__ unsigned long long act_pair_f32(unsigned long long p, float alpha) {
+  if (ACT == TLXCV_ACT_NONE) return p;
+  float lo = __uint_as_float(static_cast<uint32_t>(p)), hi = __uint_as_float(static_cast<uint32_t>(p >> 32));
+  if (ACT == TLXCV_ACT_RELU) {
+    lo = fmaxf(lo, 0.0f), hi = fmaxf(hi, 0.0f);
+  } else if (ACT == TLXCV_ACT_RELU6) {
+    lo = fminf(fmaxf(lo, 0.0f), 6.0f), hi = fminf(fmaxf(hi, 0.0f), 6.0f);
+  } else if (ACT == TLXCV_ACT_LEAKY) {
+    const uint32_t al = __float_as_uint(alpha);
+    const unsigned long long m = fmul2(p, pack_u64(al, al));
+    lo = fmaxf(lo, __uint_as_float(static_cast<uint32_t>(m))), hi = fmaxf(hi, __uint_as_float(static_cast<uint32_t>(m >> 32)));
+  }
+  return pack_u64(__float_as_uint(lo), __float_as_uint(hi));
+}
+// ReLU / ReLU6 on a packed bf16 pair (after rounding)
+template <int ACT>
+__device__ __forceinline__ uint32_t act_pair_bf16(uint32_t o) {
+  uint32_t r = o;
+  if (ACT == TLXCV_ACT_RELU || ACT == TLXCV_ACT_RELU6) asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(o), "r"(0u));
+  if (ACT == TLXCV_ACT_RELU6) asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0x40C040C0u));  // 6.0 | 6.0
+  return r;
+}
+
 // Everything one epilogue warp needs, hoisted out of the loops (kernel parameters live in constant
 // memory; re-reading them through the uniform datapath inside the item loop costs latency).
 struct EpiArgs {
@@ -192,13 +247,18 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // One epilogue warp: TMEM lane group `lg` (rows), column group `cgroup`.  The warp's work is the
 // sequence of its valid 32x32 chunks ("items") over the CTA's tiles.  Per item:
 //   tcgen05.ld -> fp32 scale/shift -> act1 -> (+ residual) -> act2 -> bf16 -> TMA store.
-// The residual chunk is fetched by TMA into a kRing-deep ring of 2 KB SWIZZLE_64B buffers three
+// The residual chunk is fetched by TMA into a kRing-deep ring of 2 KB SWIZZLE_64B buffers two
 // items ahead; each lane reads ITS row of the buffer, computes, and writes its output row back into
 // the same buffer, which one TMA store then drains.  No per-element global addressing, no
 // predicates: TMA clips the M and C_out tails.
 // DUAL: the tile has TWO accumulators (conv3 of a bottleneck and the block's downsample conv, see the kernel):
 //     y = act1( acc1 * scale + shift  +  acc2 * scale2 + shift2 )
 // the scale/shift buffer then holds [scale | scale2 | shift | shift2] for the tile's BLOCK_N = 128 channels.
+#ifdef TLXCV_EPI_OLD_REFILL  // experiment switch: residual refill right after the store commit, three items ahead
+constexpr bool kOldRefill = true;
+#else
+constexpr bool kOldRefill = false;
+#endif
 template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool DUAL = false>
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
   static_assert(!DUAL || (BLOCK_N == 128 && !RES && !F32), "dual accumulators: 128-wide bf16 tiles without a residual");
@@ -210,7 +270,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   const int swz_own = (lane >> 1) & 3;
   const uint32_t own_row = a.ring + lane * 64;
 
-  // prefetch cursor (only lane 0 advances it): walks the same item sequence, kRing-1 items ahead
+  // prefetch cursor (only lane 0 advances it): walks the same item sequence, two items ahead (one for a 2-slot ring)
   int pf_tile = a.first_tile, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0;
   uint32_t pf = 0;
   auto pf_place = [&]() {
@@ -226,7 +286,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       pf_tile += a.tile_stride;
       if (pf_tile < a.num_tiles) pf_place();
     }
-    if (pf_tile >= a.num_tiles) return;
+    if (pf_tile >= a.num_tiles || (a.ablate & 16)) return;
     const uint32_t slot = pf & (kRing - 1);
     const uint32_t bar = a.res_bar + slot * 8;
     mbar_arrive_expect_tx(bar, 2048);
@@ -237,30 +297,41 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   if (RES && lane == 0) {
     if (pf_tile < a.num_tiles) pf_place();
 #pragma unroll
-    for (int k = 0; k < kRing - 1; ++k) pf_issue();
+    for (int k = 0; k < (kOldRefill ? kRing - 1 : kRing == 4 ? 2 : 1); ++k) pf_issue();
   }
 
   uint32_t it = 0;  // items processed
   uint32_t acc = 0, acc_phase = 0;
   int tr = 0;
-  const bool tracer = a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;  // warp 2
+#ifdef TLXCV_FINE_TRACE  // per-chunk events instead of per-tile events (tools/trace_chunks.py); costs a few percent
+  const bool fine = (a.ablate & 64) != 0;
+#else
+  constexpr bool fine = false;
+#endif
+  const bool tracer = a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0 && !fine;  // warp 2
+  const bool ftracer = fine && a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;
+  float4 sc_nx = make_float4(0.f, 0.f, 0.f, 0.f), sh_nx = sc_nx, sc2_nx = sc_nx, sh2_nx = sc_nx;
+  const bool sc_lane = a.sc_mode == 1 && lane < kCpw * 8 && c_first * 32 + lane * 4 < BLOCK_N;
+  auto fetch_sc = [&](int t) {
+    const int nn0 = (t % a.n_tiles) * BLOCK_N + c_first * 32;
+    sc_nx = __ldg(reinterpret_cast<const float4*>(a.scale + nn0) + lane);
+    sh_nx = __ldg(reinterpret_cast<const float4*>(a.shift + nn0) + lane);
+    if (DUAL) {
+      sc2_nx = __ldg(reinterpret_cast<const float4*>(a.scale2 + nn0) + lane);
+      sh2_nx = __ldg(reinterpret_cast<const float4*>(a.shift2 + nn0) + lane);
+    }
+  };
+  if (sc_lane && a.first_tile < a.num_tiles) fetch_sc(a.first_tile);
   for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
     const int m_pair = tile / a.n_tiles, n_tile = tile - m_pair * a.n_tiles;
     const int m_tile = a.two ? 2 * m_pair + a.rank : m_pair;
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = max(0, min(min(kCpw, BLOCK_N / 32 - c_first), (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
-    float4 sc_pf = make_float4(0.f, 0.f, 0.f, 0.f), sh_pf = sc_pf, sc2_pf = sc_pf, sh2_pf = sc_pf;
-    const bool sc_lane = a.sc_mode == 1 && lane < kCpw * 8 && c_first * 32 + lane * 4 < BLOCK_N;
-    if (sc_lane) {
-      // this warp's slice of the tile's scale / shift: fetched now, the latency hides behind the accumulator wait
-      sc_pf = __ldg(reinterpret_cast<const float4*>(a.scale + n0 + c_first * 32) + lane);
-      sh_pf = __ldg(reinterpret_cast<const float4*>(a.shift + n0 + c_first * 32) + lane);
-      if (DUAL) {
-        sc2_pf = __ldg(reinterpret_cast<const float4*>(a.scale2 + n0 + c_first * 32) + lane);
-        sh2_pf = __ldg(reinterpret_cast<const float4*>(a.shift2 + n0 + c_first * 32) + lane);
-      }
-    }
+    // this warp's slice of the tile's scale / shift was requested one tile ago (an epilogue-bound layer finds its
+    // accumulator already complete, so a load issued here would be fully exposed); request the next tile's now
+    const float4 sc_pf = sc_nx, sh_pf = sh_nx, sc2_pf = sc2_nx, sh2_pf = sh2_nx;
+    if (sc_lane && tile + a.tile_stride < a.num_tiles) fetch_sc(tile + a.tile_stride);
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
     if (tracer) trace_c(a.trace, 2, tr);  // [3k+1] accumulator complete
@@ -292,12 +363,20 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       const int cbase = n0 + chunk * 32;
       const uint32_t slot = it & (kRing - 1);
       uint32_t v[32];
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k] chunk start
       tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + chunk * 32, v);
       uint32_t v2[DUAL ? 32 : 1];
       if (DUAL) tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + BLOCK_N + chunk * 32,
                                    reinterpret_cast<uint32_t(&)[32]>(v2));
       if (RES) {
-        mbar_wait(a.res_bar + slot * 8, (it / kRing) & 1);  // residual chunk has landed in the ring slot
+        if (kRing == 4 && !kOldRefill && lane == 0) {
+          // four slots: [it-1] draining, [it] in use, [it+1] in flight; request item it+2 into the slot item it-2 used.
+          // That store was committed a whole item ago, so this wait does not stall (waiting for the store just
+          // committed cost ~300 cycles per item), and the request still leads its use by two items.
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          pf_issue();
+        }
+        if (!(a.ablate & 16)) mbar_wait(a.res_bar + slot * 8, (it / kRing) & 1);  // residual chunk has landed in the ring slot
       } else if (!F32) {
         // the TMA store that used this slot kRing items ago must have finished reading it
         if (lane == 0) {
@@ -308,42 +387,51 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         }
         __syncwarp();
       }
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+1] residual landed / staging slot free
       tmem_ld_wait();
-      float f[32];
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+2] accumulator chunk in registers
+      if (a.ablate & 32) {  // timing experiment: accumulator read and dropped
+        if (ci == n_my - 1) {
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) release_acc();
+        }
+        if (RES && (kRing == 2 || kOldRefill) && lane == 0) pf_issue();
+        continue;
+      }
+      // fp32 pairs (two adjacent channels per 64-bit register): packed FMA / ADD / MUL halve the fp32 instruction
+      // count of this loop, which is issue-bound (two epilogue warps per scheduler)
+      unsigned long long pr[16];
       if (DUAL) {
         // sum of the two folded-BN branches in fp32, then the block's activation
-        const float4* s1p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + chunk * 32 : a.scale + cbase);
-        const float4* h1p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + 256 + chunk * 32 : a.shift + cbase);
-        const float4* s2p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + 128 + chunk * 32 : a.scale2 + cbase);
-        const float4* h2p = reinterpret_cast<const float4*>(a.sc_mode != 2 ? sc_buf + 384 + chunk * 32 : a.shift2 + cbase);
+        const ulonglong2* s1p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + chunk * 32 : a.scale + cbase);
+        const ulonglong2* h1p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + 256 + chunk * 32 : a.shift + cbase);
+        const ulonglong2* s2p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + 128 + chunk * 32 : a.scale2 + cbase);
+        const ulonglong2* h2p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + 384 + chunk * 32 : a.shift2 + cbase);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 s1 = s1p[j], h1 = h1p[j], s2 = s2p[j], h2 = h2p[j];
-          f[4 * j + 0] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 0]), s1.x, h1.x) + fmaf(__uint_as_float(v2[(4 * j + 0) % (DUAL ? 32 : 1)]), s2.x, h2.x), a.alpha1);
-          f[4 * j + 1] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 1]), s1.y, h1.y) + fmaf(__uint_as_float(v2[(4 * j + 1) % (DUAL ? 32 : 1)]), s2.y, h2.y), a.alpha1);
-          f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), s1.z, h1.z) + fmaf(__uint_as_float(v2[(4 * j + 2) % (DUAL ? 32 : 1)]), s2.z, h2.z), a.alpha1);
-          f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), s1.w, h1.w) + fmaf(__uint_as_float(v2[(4 * j + 3) % (DUAL ? 32 : 1)]), s2.w, h2.w), a.alpha1);
+          const ulonglong2 s1 = s1p[j], h1 = h1p[j], s2 = s2p[j], h2 = h2p[j];
+          pr[2 * j] = fadd2(ffma2(pack_u64(v[4 * j], v[4 * j + 1]), s1.x, h1.x),
+                            ffma2(pack_u64(v2[(4 * j) % (DUAL ? 32 : 1)], v2[(4 * j + 1) % (DUAL ? 32 : 1)]), s2.x, h2.x));
+          pr[2 * j + 1] = fadd2(ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), s1.y, h1.y),
+                                ffma2(pack_u64(v2[(4 * j + 2) % (DUAL ? 32 : 1)], v2[(4 * j + 3) % (DUAL ? 32 : 1)]), s2.y, h2.y));
         }
       } else if (a.sc_mode != 2) {
-        const float4* scp = reinterpret_cast<const float4*>(sc_buf + chunk * 32);
-        const float4* shp = reinterpret_cast<const float4*>(sc_buf + 256 + chunk * 32);
+        const ulonglong2* scp = reinterpret_cast<const ulonglong2*>(sc_buf + chunk * 32);
+        const ulonglong2* shp = reinterpret_cast<const ulonglong2*>(sc_buf + 256 + chunk * 32);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 sc = scp[j], sh = shp[j];
-          f[4 * j + 0] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x), a.alpha1);
-          f[4 * j + 1] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), a.alpha1);
-          f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), a.alpha1);
-          f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), a.alpha1);
+          const ulonglong2 sc = scp[j], sh = shp[j];
+          pr[2 * j] = ffma2(pack_u64(v[4 * j], v[4 * j + 1]), sc.x, sh.x);
+          pr[2 * j + 1] = ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), sc.y, sh.y);
         }
       } else {
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const float4 sc = __ldg(reinterpret_cast<const float4*>(a.scale + cbase) + j);
-          const float4 sh = __ldg(reinterpret_cast<const float4*>(a.shift + cbase) + j);
-          f[4 * j + 0] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 0]), sc.x, sh.x), a.alpha1);
-          f[4 * j + 1] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 1]), sc.y, sh.y), a.alpha1);
-          f[4 * j + 2] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 2]), sc.z, sh.z), a.alpha1);
-          f[4 * j + 3] = act1f<ACT1>(fmaf(__uint_as_float(v[4 * j + 3]), sc.w, sh.w), a.alpha1);
+          const ulonglong2 sc = ldg_u64x2(reinterpret_cast<const ulonglong2*>(a.scale + cbase) + j);
+          const ulonglong2 sh = ldg_u64x2(reinterpret_cast<const ulonglong2*>(a.shift + cbase) + j);
+          pr[2 * j] = ffma2(pack_u64(v[4 * j], v[4 * j + 1]), sc.x, sh.x);
+          pr[2 * j + 1] = ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), sc.y, sh.y);
         }
       }
       if (ci == n_my - 1) {
@@ -354,50 +442,74 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         __syncwarp();
         if (lane == 0) release_acc();
       }
+      // ReLU / ReLU6 commute with the rounding to bf16 (monotonic, 0 and 6 exact), so they run on packed bf16 pairs
+      // after the conversion; anything else, and an activation that precedes the residual add, runs in fp32
+      constexpr bool kAct1Packed = !RES && !F32 && (ACT1 == TLXCV_ACT_RELU || ACT1 == TLXCV_ACT_RELU6);
+      if (!kAct1Packed) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pr[j] = act_pair_f32<ACT1>(pr[j], a.alpha1);
+      }
       if (F32) {
         const int gr = m0 + lane;
         if (gr < a.M) {
           float* dst = a.out_f32 + static_cast<size_t>(gr) * a.Cout + cbase;
 #pragma unroll
           for (int j = 0; j < 8; ++j)
-            if (cbase + 4 * j < a.Cout)
-              reinterpret_cast<float4*>(dst)[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+            if (cbase + 4 * j < a.Cout) reinterpret_cast<ulonglong2*>(dst)[j] = make_ulonglong2(pr[2 * j], pr[2 * j + 1]);
         }
         continue;
       }
       const uint32_t row = own_row + slot * 2048;
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+3] scale/shift/act done (approximately: the compiler may move math)
+      uint4 rv[RES ? 4 : 1];
+      if (RES) {
+        // the four 16-byte pieces of this lane's residual row, requested back to back (volatile asm keeps program order:
+        // a load per loop iteration below would serialise load -> math -> store four times)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(rv[j % (RES ? 4 : 1)].x), "=r"(rv[j % (RES ? 4 : 1)].y), "=r"(rv[j % (RES ? 4 : 1)].z), "=r"(rv[j % (RES ? 4 : 1)].w)
+                       : "r"(row + ((j ^ swz_own) << 4)));
+      }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const uint32_t addr = row + ((j ^ swz_own) << 4);
+        uint32_t o[4];
         if (RES) {
-          uint4 val;
-          asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w) : "r"(addr));
-          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&val);
+          const uint4 val = rv[j % (RES ? 4 : 1)];
+          const uint32_t h[4] = {val.x, val.y, val.z, val.w};
+          constexpr bool kAct2Packed = ACT2 == TLXCV_ACT_RELU || ACT2 == TLXCV_ACT_RELU6;
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const float2 rr = __bfloat1622float2(h[e]);
-            f[8 * j + 2 * e] = act1f<ACT2>(f[8 * j + 2 * e] + rr.x, a.alpha2);
-            f[8 * j + 2 * e + 1] = act1f<ACT2>(f[8 * j + 2 * e + 1] + rr.y, a.alpha2);
+            unsigned long long t = fadd2(pr[4 * j + e], bf16x2_to_f32x2(h[e]));  // the add stays in fp32
+            if (!kAct2Packed) t = act_pair_f32<ACT2>(t, a.alpha2);
+            o[e] = pack_pair_bf16(t);
+            if (kAct2Packed) o[e] = act_pair_bf16<ACT2>(o[e]);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            o[e] = pack_pair_bf16(pr[4 * j + e]);
+            if (kAct1Packed) o[e] = act_pair_bf16<ACT1>(o[e]);
           }
         }
-        const uint32_t o0 = pack_bf16x2(f[8 * j + 0], f[8 * j + 1]), o1 = pack_bf16x2(f[8 * j + 2], f[8 * j + 3]);
-        const uint32_t o2 = pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), o3 = pack_bf16x2(f[8 * j + 6], f[8 * j + 7]);
         // each lane only ever touches ITS row of the slot, so no warp sync is needed between the
         // residual read and this write
-        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
+        asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       }
       fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
       __syncwarp();
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+4] staged
       if (lane == 0) {
         if (!(a.ablate & 2)) tma_store_2d(a.tmap_out, a.ring + slot * 2048, cbase, m0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (RES) {
-          // refill the slot of item it+3 (== the slot item it-1 used): every store but the one just
-          // committed must have finished reading its buffer
+        if (RES && (kRing == 2 || kOldRefill)) {
+          // two slots: refill the slot item it-1 used with item it+1 as soon as its store has read the buffer
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           pf_issue();
         }
       }
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+5] store issued, next residual requested
     }
     if (++acc == 2) {
       acc = 0;
@@ -527,6 +639,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           if constexpr (TWO) {
             // both CTAs' bytes are counted on the LEADER's full barrier, which alone is armed (for both halves)
             const uint32_t lbar = mapa_u32(bar, 0);
+            if (p.ablate & 8) {  // timing experiment: operands never loaded
+              if (rank == 0) mbar_arrive(bar);
+              ps.advance(n_stages);
+              continue;
+            }
             if (rank == 0) mbar_arrive_expect_tx(bar, 2 * kStageB);
             if (MODE == kModeTiled) {
               tma_load_2d_2sm(a_dst, &tmapA, lbar, kb * kBlockK, m0);
@@ -539,6 +656,11 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
               }
             }
             tma_load_2d_2sm(a_dst + kABytes, &tmapB, lbar, kb * kBlockK, n0 + static_cast<int>(rank) * (BLOCK_N / 2));
+            ps.advance(n_stages);
+            continue;
+          }
+          if (p.ablate & 8) {  // timing experiment: operands never loaded
+            mbar_arrive(bar);
             ps.advance(n_stages);
             continue;
           }

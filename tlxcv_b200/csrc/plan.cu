@@ -395,6 +395,10 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   }
   if (d.act2 != TLXCV_ACT_NONE && d.in1 < 0)
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: a second activation without a residual add");
+  // the tcgen05 epilogue evaluates LeakyReLU as max(v, alpha * v)
+  if ((d.act1 == TLXCV_ACT_LEAKY && !(d.alpha1 >= 0.0f && d.alpha1 <= 1.0f)) ||
+      (d.act2 == TLXCV_ACT_LEAKY && !(d.alpha2 >= 0.0f && d.alpha2 <= 1.0f)))
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: LeakyReLU slope outside [0, 1]");
   std::string err = tc_conv_prepare(op.tc, ctx->sm_count, act_in, N, H, W, C, in.cs, w, Ktot, K, R, S, stride, pad, dil,
                                     groups, force_bn, out_bf16, res_bf16);
   if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());

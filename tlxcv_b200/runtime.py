@@ -17,7 +17,8 @@ import torch
 
 from . import planner
 
-_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtlxcv_b200.so")
+# TLXCV_B200_LIB: another build of the same library (A/B timing of kernel variants on one box); never a fallback
+_LIB_PATH = os.environ.get("TLXCV_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtlxcv_b200.so")
 ABI_VERSION = 1
 
 PREC_BF16, PREC_F32 = 0, 1
