@@ -15,7 +15,7 @@
 //   B tile  BLOCK_N filters x 64 K-elements (K-major, SWIZZLE_128B) from the packed weights
 //   D       BLOCK_N fp32 TMEM columns x 128 lanes, double buffered (epilogue of tile i overlaps
 //           the main loop of tile i+1)
-// Warp roles (persistent CTA, one per SM): w0 TMA producer, w1 MMA issuer (one thread),
+// Warp roles (persistent CTA, one per SM): w0 TMA producer, w1 MMA issuer (converged warp, one elected lane),
 // w2 TMEM allocator, w4-7 epilogue (TMEM -> registers -> smem transpose -> coalesced 16 B stores),
 // w8-11 gather producers (kModeGatherC4 only).
 #include <algorithm>
@@ -109,19 +109,37 @@ __device__ __forceinline__ void tma_load_im2col_4d_2sm(uint32_t dst, const CUten
       "l"(reinterpret_cast<uint64_t>(m)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
       : "memory");
 }
-__device__ __forceinline__ void umma_bf16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
 // arrive on the barrier at this offset in BOTH CTAs of the pair when all MMAs issued so far have completed
 __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
                "h"(static_cast<uint16_t>(3))
                : "memory");
+}
+// tcgen05.mma with the descriptors given as (low word, shared high word): no 64-bit arithmetic in the issue loop
+template <bool kTwo>
+__device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, uint32_t b_lo, uint32_t hi, uint32_t idesc,
+                                               uint32_t accumulate) {
+  if (kTwo)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %3};\n\tmov.b64 db, {%2, %3};\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %4, p;\n\t}" ::"r"(tmem_d),
+        "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+  return pred != 0;
 }
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst) {
@@ -693,17 +711,24 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer (one thread) =====================
-    if (lane == 0 && rank == 0) {  // in a CTA pair only the leader issues
+    // ===================== MMA issuer: the warp stays converged, one elected lane issues =====================
+    // (issued from a divergent `lane == 0` branch, every tcgen05.mma operand went through an ELECT + R2UR "waterfall"
+    // loop: ~100 cycles per instruction, which bounded every 64/128-wide tile; in a converged warp the descriptors
+    // live in uniform registers)
+    if (rank == 0) {  // in a CTA pair only the leader issues
       constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * kBlockM : kBlockM, BLOCK_N);
+      // make_kmajor_sw128_desc split in words: high = SBO 1024 B | version 1 | SWIZZLE_128B, low = address >> 4 | LBO 1
+      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);  // descriptor low word of stage 0
+      const bool tracer1 = lane == 0;
       PipeState ps;
       uint32_t acc = 0, acc_phase = 0;
       int tr = 0;
       for (int tile = worker; tile < num_tiles; tile += n_workers) {
-        trace_c(p.trace, 1, tr);  // [4k] tile start
+        if (tracer1) trace_c(p.trace, 1, tr);  // [4k] tile start
         mbar_wait(smem_u32(&tmem_empty_bar[acc]), acc_phase ^ 1);
         tcgen05_fence_after();
-        trace_c(p.trace, 1, tr);  // [4k+1] accumulator free
+        if (tracer1) trace_c(p.trace, 1, tr);  // [4k+1] accumulator free
         const uint32_t tmem_d1 = tmem_base + acc * kAccCols;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           const bool second = DUAL && kb >= p.num_kb1;
@@ -711,32 +736,37 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           const int kbl = second ? kb - p.num_kb1 : kb;  // first K block of an accumulator overwrites it
           mbar_wait(smem_u32(&full_bar[ps.stage]), ps.phase);
           tcgen05_fence_after();
-          if (kb == 0) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
-          const uint32_t a_addr = smem_u32(smem + ps.stage * kStageB);
-          const uint64_t adesc = make_kmajor_sw128_desc(a_addr);
-          const uint64_t bdesc = make_kmajor_sw128_desc(a_addr + kABytes);
+          if (kb == 0 && tracer1) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
+          const uint32_t a_lo = smem_lo + static_cast<uint32_t>(ps.stage) * (kStageB >> 4);
+          const uint32_t b_lo = a_lo + (kABytes >> 4);
+          if (elect_one_sync()) {
+            if (!(p.ablate & 4)) {
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-            if (p.ablate & 4) continue;
+              for (int k = 0; k < kBlockK / 16; ++k) {
+                // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+                if (k == 0)
+                  umma_bf16_lohi<TWO>(tmem_d, a_lo, b_lo, desc_hi, idesc, kbl != 0);
+                else
+                  umma_bf16_lohi<TWO>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
+              }
+            }
+            // frees the smem stage (of both CTAs of a pair) when these MMAs retire
             if (TWO)
-              umma_bf16_2sm(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kbl | k) != 0);
+              umma_commit_2sm(smem_u32(&empty_bar[ps.stage]));
             else
-              umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kbl | k) != 0);
+              umma_commit(smem_u32(&empty_bar[ps.stage]));
+            // accumulator ready for the epilogue (of both CTAs of a pair)
+            if (kb == p.num_kb - 1) {
+              if (TWO)
+                umma_commit_2sm(smem_u32(&tmem_full_bar[acc]));
+              else
+                umma_commit(smem_u32(&tmem_full_bar[acc]));
+            }
           }
-          // frees the smem stage (of both CTAs of a pair) when these MMAs retire
-          if (TWO)
-            umma_commit_2sm(smem_u32(&empty_bar[ps.stage]));
-          else
-            umma_commit(smem_u32(&empty_bar[ps.stage]));
+          __syncwarp();
           ps.advance(n_stages);
         }
-        // accumulator ready for the epilogue (of both CTAs of a pair)
-        if (TWO)
-          umma_commit_2sm(smem_u32(&tmem_full_bar[acc]));
-        else
-          umma_commit(smem_u32(&tmem_full_bar[acc]));
-        trace_c(p.trace, 1, tr);  // [4k+3] all MMAs of the tile issued
+        if (tracer1) trace_c(p.trace, 1, tr);  // [4k+3] all MMAs of the tile issued
         if (++acc == 2) {
           acc = 0;
           acc_phase ^= 1;
