@@ -136,6 +136,15 @@ __device__ __forceinline__ void umma_bf16_lohi(uint32_t tmem_d, uint32_t a_lo, u
         "r"(a_lo), "r"(b_lo), "r"(hi), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// non-blocking mbarrier phase test, warp-uniform result (all lanes must see the phase complete)
+__device__ __forceinline__ bool mbar_test_all(uint32_t bar, uint32_t phase) {
+  uint32_t ok;
+  asm volatile("{\n\t.reg .pred P;\n\tmbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}"
+               : "=r"(ok)
+               : "r"(bar), "r"(phase)
+               : "memory");
+  return __all_sync(0xffffffffu, ok != 0);
+}
 __device__ __forceinline__ bool elect_one_sync() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -720,7 +729,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       // make_kmajor_sw128_desc split in words: high = SBO 1024 B | version 1 | SWIZZLE_128B, low = address >> 4 | LBO 1
       constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
       const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);  // descriptor low word of stage 0
-      const bool tracer1 = lane == 0;
+      const bool tracer1 = lane == 0 && p.trace != nullptr;
+      const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+      const int num_kb = p.num_kb, num_kb1 = p.num_kb1;
+      const bool no_mma = (p.ablate & 4) != 0;
       PipeState ps;
       uint32_t acc = 0, acc_phase = 0;
       int tr = 0;
@@ -730,33 +742,49 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         tcgen05_fence_after();
         if (tracer1) trace_c(p.trace, 1, tr);  // [4k+1] accumulator free
         const uint32_t tmem_d1 = tmem_base + acc * kAccCols;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          const bool second = DUAL && kb >= p.num_kb1;
-          const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
-          const int kbl = second ? kb - p.num_kb1 : kb;  // first K block of an accumulator overwrites it
-          mbar_wait(smem_u32(&full_bar[ps.stage]), ps.phase);
+        // Up to two K blocks per round: this warp shares its scheduler with two epilogue warps, and the fixed cost of a round
+        // (barrier poll, fence, election, uniform-register setup, commit) otherwise exceeds the 256 tensor-core cycles
+        // of a 128-wide K block.
+        for (int kb = 0; kb < num_kb;) {
+          const uint32_t st0 = ps.stage;
+          mbar_wait(full0 + st0 * 8, ps.phase);
+          ps.advance(n_stages);
+          const uint32_t st1 = ps.stage;
+          // the next K block joins this round only if its operands have landed already (never wait for it: with three
+          // 48 KB stages the loads are the critical path)
+          const bool two_kb = kb + 1 < num_kb && mbar_test_all(full0 + st1 * 8, ps.phase);
+          if (two_kb) ps.advance(n_stages);
           tcgen05_fence_after();
           if (kb == 0 && tracer1) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
-          const uint32_t a_lo = smem_lo + static_cast<uint32_t>(ps.stage) * (kStageB >> 4);
-          const uint32_t b_lo = a_lo + (kABytes >> 4);
           if (elect_one_sync()) {
-            if (!(p.ablate & 4)) {
 #pragma unroll
-              for (int k = 0; k < kBlockK / 16; ++k) {
-                // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-                if (k == 0)
-                  umma_bf16_lohi<TWO>(tmem_d, a_lo, b_lo, desc_hi, idesc, kbl != 0);
-                else
-                  umma_bf16_lohi<TWO>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
+            for (int h = 0; h < 2; ++h) {
+              if (h == 1 && !two_kb) break;
+              const int kk = kb + h;
+              const uint32_t st = h ? st1 : st0;
+              const bool second = DUAL && kk >= num_kb1;
+              const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
+              const int kbl = second ? kk - num_kb1 : kk;  // first K block of an accumulator overwrites it
+              const uint32_t a_lo = smem_lo + st * (kStageB >> 4);
+              const uint32_t b_lo = a_lo + (kABytes >> 4);
+              if (!no_mma) {
+#pragma unroll
+                for (int k = 0; k < kBlockK / 16; ++k) {
+                  // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+                  if (k == 0)
+                    umma_bf16_lohi<TWO>(tmem_d, a_lo, b_lo, desc_hi, idesc, kbl != 0);
+                  else
+                    umma_bf16_lohi<TWO>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
+                }
               }
+              // frees the smem stage (of both CTAs of a pair) when these MMAs retire
+              if (TWO)
+                umma_commit_2sm(empty0 + st * 8);
+              else
+                umma_commit(empty0 + st * 8);
             }
-            // frees the smem stage (of both CTAs of a pair) when these MMAs retire
-            if (TWO)
-              umma_commit_2sm(smem_u32(&empty_bar[ps.stage]));
-            else
-              umma_commit(smem_u32(&empty_bar[ps.stage]));
             // accumulator ready for the epilogue (of both CTAs of a pair)
-            if (kb == p.num_kb - 1) {
+            if (kb + (two_kb ? 2 : 1) >= num_kb) {
               if (TWO)
                 umma_commit_2sm(smem_u32(&tmem_full_bar[acc]));
               else
@@ -764,7 +792,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             }
           }
           __syncwarp();
-          ps.advance(n_stages);
+          kb += two_kb ? 2 : 1;
         }
         if (tracer1) trace_c(p.trace, 1, tr);  // [4k+3] all MMAs of the tile issued
         if (++acc == 2) {
@@ -1067,7 +1095,9 @@ void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_b
   // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
   p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps, two) == stages_for(block_n, p.ring, 1, p.epi_warps, two)) ? 2 : 1;
   if (const char* e = getenv("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
+  if (const char* e = getenv("TLXCV_DEBUG_RING")) p.ring = (atoi(e) == 4 && out_bf16) ? 4 : 2;  // A/B timing only
   p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
+  if (const char* e = getenv("TLXCV_DEBUG_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));  // A/B timing only
 }
 
 }  // namespace

@@ -24,6 +24,19 @@ LAYERS = [  # name, cin, cout, hw, k, stride, res, env
     ("l3conv2", 256, 256, 14, 3, 1, False, {}),
     ("l3conv2_nopair", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_2SM": "0"}),
     ("l2conv2", 128, 128, 28, 3, 1, False, {}),
+    ("l2conv2_pair", 128, 128, 28, 3, 1, False, {"TLXCV_DEBUG_2SM": "1"}),
+    ("l2conv1", 512, 128, 28, 1, 1, False, {}),
+    ("l2conv1_pair", 512, 128, 28, 1, 1, False, {"TLXCV_DEBUG_2SM": "1"}),
+    ("l4conv2", 512, 512, 7, 3, 1, False, {}),
+    ("l4conv2_pair", 512, 512, 7, 3, 1, False, {"TLXCV_DEBUG_2SM": "1"}),
+    ("l2conv2_s2", 128, 128, 28, 3, 1, False, {"TLXCV_DEBUG_STAGES": "2"}),
+    ("l2conv2_s3", 128, 128, 28, 3, 1, False, {"TLXCV_DEBUG_STAGES": "3"}),
+    ("l2conv2_s4", 128, 128, 28, 3, 1, False, {"TLXCV_DEBUG_STAGES": "4"}),
+    ("l2conv2_r2", 128, 128, 28, 3, 1, False, {"TLXCV_DEBUG_RING": "2"}),
+    ("l2conv2_pair_r2", 128, 128, 28, 3, 1, False, {"TLXCV_DEBUG_2SM": "1", "TLXCV_DEBUG_RING": "2"}),
+    ("l3conv2_s2", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_STAGES": "2"}),
+    ("l3conv2_s3", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_STAGES": "3"}),
+    ("l3conv2_r4", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_RING": "4"}),
 ]
 ABLATIONS = [int(x) for x in os.environ.get("ABLATIONS", "0,2,16,18,8,24,26,32,40,56,4,12").split(",")]
 
@@ -79,10 +92,11 @@ def main():
                 best = us if best is None else min(best, us)
             row.append(f"{ab}:{best:.1f}")
             kern = convs[-1]["kernel"]
+            stages = (convs[-1]["smem"] - 70000) // (49152 if "n256" in kern else 32768 if "n128" in kern else 24576) if "2sm" not in kern else -1
             del plan, outs, net
             for kk in env:
                 os.environ.pop(kk, None)
-        print(f"{name:16s} {kern:28s} " + "  ".join(row), flush=True)
+        print(f"{name:16s} {kern:28s} st{stages} " + "  ".join(row), flush=True)
     os.environ.pop("TLXCV_DEBUG_ABLATE", None)
 
 
