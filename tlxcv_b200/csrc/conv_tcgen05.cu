@@ -524,7 +524,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         // residual read and this write
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       }
-      fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
+      if (!(a.ablate & 128)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
       __syncwarp();
       if (ftracer) trace_c(a.trace, 2, tr);  // [6k+4] staged
       if (lane == 0) {
