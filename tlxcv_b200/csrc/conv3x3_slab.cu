@@ -530,8 +530,16 @@ std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat1
     const long long items = static_cast<long long>(p.cblocks) * N * bands * p.segs;
     const long long per_cta = (items + sm_count - 1) / sm_count;
     const long long steps = (rows + p.T - 1) / p.T;
-    const long long cost = per_cta * (steps * 10 + 6 * p.ng + 4);  // steps + ring warm-up + band overhead
+    // steps + 0.6 step per band: fitted to bs256 timings (dense 56x56: 1/2/4/7/14 bands = 93/93/85/91/97 us; grouped
+    // 56x56: 167/150/156/173/214 us; grouped 28x28: 97/120/153/203 us) - the producer runs ahead across items, so a
+    // band costs little beyond its halo rows, and finer bands balance the 148 CTAs better
+    const long long cost = per_cta * (steps * 10 + 6);
     if (best < 0 || cost < best) best = cost, p.bands = bands, p.band_rows = rows;
+  }
+  if (const char* e = getenv("TLXCV_DEBUG_SLAB_BANDS")) {  // A/B timing only
+    const int bands = std::max(1, std::min(H, atoi(e)));
+    p.band_rows = (H + bands - 1) / bands;
+    p.bands = (H + p.band_rows - 1) / p.band_rows;
   }
   L.grid = static_cast<int>(std::min<long long>(static_cast<long long>(p.cblocks) * N * p.bands * p.segs, sm_count));
   L.block_n = kBlockN;

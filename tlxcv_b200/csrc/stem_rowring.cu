@@ -650,8 +650,15 @@ std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry
     const long long items = static_cast<long long>(N) * bands * p.q_tiles;
     const long long per_cta = (items + sm_count - 1) / sm_count;
     const long long steps = pool ? rows + 1 : (rows + kT - 1) / kT;
-    const long long cost = per_cta * (steps * 10 + p.ng * 6 + 8);  // steps + ring warm-up + band overhead
+    // steps + 0.4 step per band, fitted to bs256/512 timings (ResNet stem 1/2/4/8 bands = 186/190/174/184 us, MobileNet
+    // stem 220/197/201/211 us): the producer runs ahead across items, a band costs little beyond its halo rows
+    const long long cost = per_cta * (steps * 10 + 4);
     if (best < 0 || cost < best) best = cost, p.bands = bands, p.band_rows = rows;
+  }
+  if (const char* e = getenv("TLXCV_DEBUG_STEM_BANDS")) {  // A/B timing only
+    const int bands = std::max(1, std::min(units, atoi(e)));
+    p.band_rows = (units + bands - 1) / bands;
+    p.bands = (units + p.band_rows - 1) / p.band_rows;
   }
   const long long items = static_cast<long long>(N) * p.bands * p.q_tiles;
   L.grid = static_cast<int>(std::min<long long>(items, sm_count));
