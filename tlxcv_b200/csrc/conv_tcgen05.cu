@@ -231,11 +231,15 @@ __device__ __forceinline__ unsigned long long act_pair_f32(unsigned long long p,
   }
   return pack_u64(__float_as_uint(lo), __float_as_uint(hi));
 }
-// ReLU / ReLU6 on a packed bf16 pair (after rounding)
+// fp32 pair -> packed bf16 pair with ReLU / ReLU6 applied after the rounding: cvt.rn.relu clamps in the conversion
+// itself (one instruction per pair), ReLU6 adds a packed min
 template <int ACT>
-__device__ __forceinline__ uint32_t act_pair_bf16(uint32_t o) {
-  uint32_t r = o;
-  if (ACT == TLXCV_ACT_RELU || ACT == TLXCV_ACT_RELU6) asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(o), "r"(0u));
+__device__ __forceinline__ uint32_t pack_pair_bf16_act(unsigned long long p) {
+  if (ACT != TLXCV_ACT_RELU && ACT != TLXCV_ACT_RELU6) return pack_pair_bf16(p);
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;"
+      : "=r"(r)
+      : "f"(__uint_as_float(static_cast<uint32_t>(p >> 32))), "f"(__uint_as_float(static_cast<uint32_t>(p))));
   if (ACT == TLXCV_ACT_RELU6) asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0x40C040C0u));  // 6.0 | 6.0
   return r;
 }
@@ -280,7 +284,7 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // predicates: TMA clips the M and C_out tails.
 // DUAL: the tile has TWO accumulators (conv3 of a bottleneck and the block's downsample conv, see the kernel):
 //     y = act1( acc1 * scale + shift  +  acc2 * scale2 + shift2 )
-// the scale/shift buffer then holds [scale | scale2 | shift | shift2] for the tile's BLOCK_N = 128 channels.
+// the scale/shift buffer then holds [scale | scale2 | shift + shift2] for the tile's BLOCK_N = 128 channels.
 #ifdef TLXCV_EPI_OLD_REFILL  // experiment switch: residual refill right after the store commit, three items ahead
 constexpr bool kOldRefill = true;
 #else
@@ -371,8 +375,10 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         reinterpret_cast<float4*>(sc_buf + c_first * 32)[lane] = sc_pf;
         reinterpret_cast<float4*>(sc_buf + 256 + c_first * 32)[lane] = sh_pf;
         if (DUAL) {
+          // the two branches' shifts are only ever used as a sum: add them once per tile here, not once per element
           reinterpret_cast<float4*>(sc_buf + 128 + c_first * 32)[lane] = sc2_pf;
-          reinterpret_cast<float4*>(sc_buf + 384 + c_first * 32)[lane] = sh2_pf;
+          reinterpret_cast<float4*>(sc_buf + 256 + c_first * 32)[lane] =
+              make_float4(sh_pf.x + sh2_pf.x, sh_pf.y + sh2_pf.y, sh_pf.z + sh2_pf.z, sh_pf.w + sh2_pf.w);
         }
       }
       __syncwarp();
@@ -430,18 +436,33 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       // count of this loop, which is issue-bound (two epilogue warps per scheduler)
       unsigned long long pr[16];
       if (DUAL) {
-        // sum of the two folded-BN branches in fp32, then the block's activation
-        const ulonglong2* s1p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + chunk * 32 : a.scale + cbase);
-        const ulonglong2* h1p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + 256 + chunk * 32 : a.shift + cbase);
-        const ulonglong2* s2p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + 128 + chunk * 32 : a.scale2 + cbase);
-        const ulonglong2* h2p = reinterpret_cast<const ulonglong2*>(a.sc_mode != 2 ? sc_buf + 384 + chunk * 32 : a.shift2 + cbase);
+        // sum of the two folded-BN branches in fp32, then the block's activation:
+        //   acc1 * s1 + (acc2 * s2 + (h1 + h2))
+        if (a.sc_mode != 2) {
+          const ulonglong2* s1p = reinterpret_cast<const ulonglong2*>(sc_buf + chunk * 32);
+          const ulonglong2* s2p = reinterpret_cast<const ulonglong2*>(sc_buf + 128 + chunk * 32);
+          const ulonglong2* hp = reinterpret_cast<const ulonglong2*>(sc_buf + 256 + chunk * 32);  // h1 + h2
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const ulonglong2 s1 = s1p[j], h1 = h1p[j], s2 = s2p[j], h2 = h2p[j];
-          pr[2 * j] = fadd2(ffma2(pack_u64(v[4 * j], v[4 * j + 1]), s1.x, h1.x),
-                            ffma2(pack_u64(v2[(4 * j) % (DUAL ? 32 : 1)], v2[(4 * j + 1) % (DUAL ? 32 : 1)]), s2.x, h2.x));
-          pr[2 * j + 1] = fadd2(ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), s1.y, h1.y),
-                                ffma2(pack_u64(v2[(4 * j + 2) % (DUAL ? 32 : 1)], v2[(4 * j + 3) % (DUAL ? 32 : 1)]), s2.y, h2.y));
+          for (int j = 0; j < 8; ++j) {
+            const ulonglong2 s1 = s1p[j], s2 = s2p[j], h = hp[j];
+            pr[2 * j] = ffma2(pack_u64(v[4 * j], v[4 * j + 1]), s1.x,
+                              ffma2(pack_u64(v2[(4 * j) % (DUAL ? 32 : 1)], v2[(4 * j + 1) % (DUAL ? 32 : 1)]), s2.x, h.x));
+            pr[2 * j + 1] = ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), s1.y,
+                                  ffma2(pack_u64(v2[(4 * j + 2) % (DUAL ? 32 : 1)], v2[(4 * j + 3) % (DUAL ? 32 : 1)]), s2.y, h.y));
+          }
+        } else {
+          const ulonglong2* s1p = reinterpret_cast<const ulonglong2*>(a.scale + cbase);
+          const ulonglong2* h1p = reinterpret_cast<const ulonglong2*>(a.shift + cbase);
+          const ulonglong2* s2p = reinterpret_cast<const ulonglong2*>(a.scale2 + cbase);
+          const ulonglong2* h2p = reinterpret_cast<const ulonglong2*>(a.shift2 + cbase);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const ulonglong2 s1 = ldg_u64x2(s1p + j), h1 = ldg_u64x2(h1p + j), s2 = ldg_u64x2(s2p + j), h2 = ldg_u64x2(h2p + j);
+            pr[2 * j] = ffma2(pack_u64(v[4 * j], v[4 * j + 1]), s1.x,
+                              ffma2(pack_u64(v2[(4 * j) % (DUAL ? 32 : 1)], v2[(4 * j + 1) % (DUAL ? 32 : 1)]), s2.x, fadd2(h1.x, h2.x)));
+            pr[2 * j + 1] = ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), s1.y,
+                                  ffma2(pack_u64(v2[(4 * j + 2) % (DUAL ? 32 : 1)], v2[(4 * j + 3) % (DUAL ? 32 : 1)]), s2.y, fadd2(h1.y, h2.y)));
+          }
         }
       } else if (a.sc_mode != 2) {
         const ulonglong2* scp = reinterpret_cast<const ulonglong2*>(sc_buf + chunk * 32);
@@ -510,14 +531,12 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
           for (int e = 0; e < 4; ++e) {
             unsigned long long t = fadd2(pr[4 * j + e], bf16x2_to_f32x2(h[e]));  // the add stays in fp32
             if (!kAct2Packed) t = act_pair_f32<ACT2>(t, a.alpha2);
-            o[e] = pack_pair_bf16(t);
-            if (kAct2Packed) o[e] = act_pair_bf16<ACT2>(o[e]);
+            o[e] = kAct2Packed ? pack_pair_bf16_act<ACT2>(t) : pack_pair_bf16(t);
           }
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            o[e] = pack_pair_bf16(pr[4 * j + e]);
-            if (kAct1Packed) o[e] = act_pair_bf16<ACT1>(o[e]);
+            o[e] = kAct1Packed ? pack_pair_bf16_act<ACT1>(pr[4 * j + e]) : pack_pair_bf16(pr[4 * j + e]);
           }
         }
         // each lane only ever touches ITS row of the slot, so no warp sync is needed between the
@@ -1206,7 +1225,9 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // (measured on B200, bs256: 14x14 maps 1024->256 35.8 -> 33.8 us, 512->1024 58.4 -> 54.3 us; 7x7 maps with their 98
   //  M tiles lose 3-5 %: pairs halve the number of schedulable units)
   const bool pairable = (block_n == 256 || block_n == 128) && groups == 1 && mode != kModeGatherC4 && out_bf16 != nullptr;
-  bool two = pairable && block_n == 256 && p.num_kb >= 8 && p.m_tiles >= 256;  // 128-wide pairs measured: no gain
+  // 128-wide pairs measured: no gain.  Few M tiles (7x7 maps: 98) pair only with a long K loop: bs256 512->512 3x3
+  // 63.5 -> 57.3 us, 2048->512 33.8 -> 31.7 us, but 512->2048 + residual (8 K blocks) 38.9 -> 43.9 us.
+  bool two = pairable && block_n == 256 && ((p.num_kb >= 8 && p.m_tiles >= 256) || (p.num_kb >= 16 && p.m_tiles >= 64));
   if (const char* e = getenv("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && p.m_tiles >= 2;
   L.two = two ? 1 : 0;
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two);
