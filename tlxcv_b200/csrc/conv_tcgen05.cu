@@ -302,10 +302,14 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   const uint32_t own_row = a.ring + lane * 64;
 
   // prefetch cursor (only lane 0 advances it): walks the same item sequence, two items ahead (one for a 2-slot ring)
-  int pf_tile = a.first_tile, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0;
+  // (m_pair, n_tile) of a tile index advance incrementally by (dm, dn) per tile_stride: an integer division per tile
+  // costs this warp ~200 dependent cycles, three of them were 8 % of a short-K tile
+  const int dm = a.tile_stride / a.n_tiles, dn = a.tile_stride - dm * a.n_tiles;
+  const int first_m = a.first_tile / a.n_tiles, first_n = a.first_tile - first_m * a.n_tiles;
+  int pf_tile = a.first_tile, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0, pf_mp = first_m, pf_nt = first_n;
   uint32_t pf = 0;
   auto pf_place = [&]() {
-    const int m_pair = pf_tile / a.n_tiles, n_tile = pf_tile - m_pair * a.n_tiles;
+    const int m_pair = pf_mp, n_tile = pf_nt;
     const int m_tile = a.two ? 2 * m_pair + a.rank : m_pair;
     pf_m0 = m_tile * kBlockM + lg * 32;
     pf_n0 = n_tile * BLOCK_N;
@@ -315,6 +319,8 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     while (pf_tile < a.num_tiles && pf_ci >= pf_nmy) {
       pf_ci = 0;
       pf_tile += a.tile_stride;
+      pf_mp += dm, pf_nt += dn;
+      if (pf_nt >= a.n_tiles) pf_nt -= a.n_tiles, ++pf_mp;
       if (pf_tile < a.num_tiles) pf_place();
     }
     if (pf_tile >= a.num_tiles || (a.ablate & 16)) return;
@@ -340,11 +346,13 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   constexpr bool fine = false;
 #endif
   const bool tracer = a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0 && !fine;  // warp 2
-  const bool ftracer = fine && a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;
+  const bool btrace = fine && (a.ablate & 256) != 0;  // tile-boundary events instead of per-chunk events
+  const bool ftracer = fine && !btrace && a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;
+  const bool btracer = btrace && a.trace != nullptr && lg == 2 && cgroup == 0 && lane == 0;
   float4 sc_nx = make_float4(0.f, 0.f, 0.f, 0.f), sh_nx = sc_nx, sc2_nx = sc_nx, sh2_nx = sc_nx;
   const bool sc_lane = a.sc_mode == 1 && lane < kCpw * 8 && c_first * 32 + lane * 4 < BLOCK_N;
-  auto fetch_sc = [&](int t) {
-    const int nn0 = (t % a.n_tiles) * BLOCK_N + c_first * 32;
+  auto fetch_sc = [&](int nt) {  // nt: N tile index
+    const int nn0 = nt * BLOCK_N + c_first * 32;
     sc_nx = __ldg(reinterpret_cast<const float4*>(a.scale + nn0) + lane);
     sh_nx = __ldg(reinterpret_cast<const float4*>(a.shift + nn0) + lane);
     if (DUAL) {
@@ -352,19 +360,24 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       sh2_nx = __ldg(reinterpret_cast<const float4*>(a.shift2 + nn0) + lane);
     }
   };
-  if (sc_lane && a.first_tile < a.num_tiles) fetch_sc(a.first_tile);
+  if (sc_lane && a.first_tile < a.num_tiles) fetch_sc(first_n);
+  int m_pair = first_m - dm, n_tile = first_n - dn;  // advanced at the top of every iteration
   for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
-    const int m_pair = tile / a.n_tiles, n_tile = tile - m_pair * a.n_tiles;
+    m_pair += dm, n_tile += dn;
+    if (n_tile >= a.n_tiles) n_tile -= a.n_tiles, ++m_pair;
     const int m_tile = a.two ? 2 * m_pair + a.rank : m_pair;
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = max(0, min(min(kCpw, BLOCK_N / 32 - c_first), (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
     if (tracer) trace_c(a.trace, 2, tr);  // [3k] tile start
+    if (btracer) trace_c(a.trace, 2, tr);  // [5k] tile start
     // this warp's slice of the tile's scale / shift was requested one tile ago (an epilogue-bound layer finds its
     // accumulator already complete, so a load issued here would be fully exposed); request the next tile's now
     const float4 sc_pf = sc_nx, sh_pf = sh_nx, sc2_pf = sc2_nx, sh2_pf = sh2_nx;
-    if (sc_lane && tile + a.tile_stride < a.num_tiles) fetch_sc(tile + a.tile_stride);
+    if (sc_lane && tile + a.tile_stride < a.num_tiles) fetch_sc(n_tile + dn >= a.n_tiles ? n_tile + dn - a.n_tiles : n_tile + dn);
+    if (btracer) trace_c(a.trace, 2, tr);  // [5k+1] tile set-up done
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
+    if (btracer) trace_c(a.trace, 2, tr);  // [5k+2] accumulator complete
     if (tracer) trace_c(a.trace, 2, tr);  // [3k+1] accumulator complete
     float* sc_buf = const_cast<float*>(a.sc_cache) + (a.sc_mode == 1 ? acc * 512 : 0);
     if (a.sc_mode == 1) {
@@ -390,6 +403,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         mbar_arrive(a.tmem_empty_bar + acc * 8);
     };
     if (n_my == 0 && lane == 0) release_acc();  // nothing to read: release at once
+    if (btracer) trace_c(a.trace, 2, tr);  // [5k+3] scale/shift staged, chunk loop starts
 #pragma unroll 1
     for (int ci = 0; ci < n_my; ++ci, ++it) {
       const int chunk = c_first + ci;
@@ -557,6 +571,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       }
       if (ftracer) trace_c(a.trace, 2, tr);  // [6k+5] store issued, next residual requested
     }
+    if (btracer) trace_c(a.trace, 2, tr);  // [5k+4] chunk loop done
     if (++acc == 2) {
       acc = 0;
       acc_phase ^= 1;
