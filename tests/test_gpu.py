@@ -451,6 +451,51 @@ def test_resnet50_bs256_batch_invariance_and_predict():
     assert pred.dtype == torch.int64 and torch.equal(pred, full.argmax(1))
 
 
+@pytest.mark.parametrize("name,batch,size,uniq", [("mobilenet_v2", 512, 224, 32), ("resnext50_32x4d", 256, 224, 32),
+                                                  ("darknet53_det", 64, 608, 4)])
+def test_full_size_configs_batch_invariance(name, batch, size, uniq):
+    """The other BASELINE.json configurations at their full sizes (MobileNetV2 bs512, ResNeXt-50 32x4d bs256, DarkNet-53
+    bs64 at 608x608): a batch made of `uniq` distinct images repeated must give bit-identical results for every copy
+    (the kernels picked for the full-size plan treat images independently), and agree with the `uniq`-image plan that the
+    oracle tests pin (other tile shapes there: same math, other summation order)."""
+    from tlxcv_b200 import models
+    from tlxcv_b200.testing import seeded_state_dict, synthetic_images
+
+    m = models.REGISTRY[name]()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), name))
+    m = m.cuda().set_eval()
+    small = synthetic_images(uniq, size, seed=11).cuda()
+    x = small.repeat(batch // uniq, 1, 1, 1).contiguous()
+    as_list = lambda y: list(y) if isinstance(y, (list, tuple)) else [y]
+    full = as_list(m({"images": x}) if name == "darknet53_det" else m(x))
+    part = as_list(m({"images": small}) if name == "darknet53_det" else m(small))
+    for f, q in zip(full, part):
+        assert f.shape[0] == batch and bool(torch.isfinite(f).all())
+        assert torch.equal(f[:uniq], f[uniq:2 * uniq]) and torch.equal(f[:uniq], f[batch - uniq:])
+        scale = max(1.0, float(q.abs().max()))
+        assert float((f[:uniq] - q).abs().max()) <= 2.0 ** -6 * scale
+
+
+def test_leaky_relu_slope_outside_unit_interval_is_refused():
+    """The tcgen05 epilogue evaluates LeakyReLU as max(v, slope * v): the planner must refuse slopes outside [0, 1]
+    loudly instead of computing something else."""
+    from tlxcv_b200 import nn, runtime
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv = nn.GroupConv2d(in_channels=64, out_channels=64, kernel_size=1, padding=0, b_init=None)
+            self.bn = nn.BatchNorm2d(num_features=64)
+            self.act = nn.LeakyReLU(1.5)
+
+        def forward(self, x):
+            return self.act(self.bn(self.conv(x)))
+
+    net = Net().cuda().set_eval()
+    with pytest.raises(runtime.B200RuntimeError, match="LeakyReLU slope"):
+        net(torch.randn(2, 64, 8, 8, device="cuda"))
+
+
 def test_weight_update_rebuilds_the_plan():
     from tlxcv_b200 import models
 
