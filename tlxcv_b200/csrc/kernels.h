@@ -108,7 +108,7 @@ struct StemParams {
 };
 
 struct StemLaunch {
-  CUtensorMap tmapA, tmapB;
+  CUtensorMap tmapA, tmapB, tmapOut;
   StemParams p;
   int block_n, grid, threads, smem;
 };

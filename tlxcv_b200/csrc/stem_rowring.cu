@@ -82,6 +82,13 @@ __device__ __forceinline__ void umma_bf16_lo(uint32_t tmem_d, uint32_t a_lo, uin
       : "memory");
 }
 
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, uint32_t src, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+               : "memory");
+}
+
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
@@ -142,7 +149,8 @@ __host__ __device__ constexpr int chain_block(int i) {
 
 template <int BLOCK_N, int R, int SV>
 __global__ void __launch_bounds__(kThreadsS, 1)
-stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB, const StemParams p) {
+stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                    const __grid_constant__ CUtensorMap tmapOut, const StemParams p) {
   using C = SCfg<BLOCK_N>;
   constexpr int kRowBytes = C::kRowBytes;
   constexpr int kChunks = kRowBytes / 16;  // 16-byte chunks per window in one output row (4 or 8)
@@ -317,6 +325,9 @@ stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       for (int m = 0; m < it.steps; ++m) {
         const int cs = it.c0 + m * kT;
         const int c = cs + ch;  // this warp's conv row
+        // the row buffers written now were last used two steps ago: their TMA stores (unpooled stems) must have
+        // finished reading shared memory; only the issuing thread tracks them, the barrier publishes it
+        if (!p.pool && et == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         epi_bar_sync();         // the previous step's consumers are done with the row buffers
         mbar_wait(smem_u32(&tfull_bar[acc]), acc_phase);
         tcgen05_fence_after();
@@ -359,9 +370,22 @@ stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           }
         }
         if (++acc == kAccBufs) acc = 0, acc_phase ^= 1;
+        if (!p.pool) fence_proxy_async_smem();  // the rows are read by TMA stores below
         epi_bar_sync();  // both conv rows of the step are complete in their buffers
         if (p.ablate & 8) continue;
-        if (!p.pool) {
+        if (!p.pool && !(p.ablate & 32)) {
+          // One TMA store per conv row, issued by one thread: the row buffer already is the SWIZZLE_64B / 128B image of
+          // [128 windows][BLOCK_N channels], and the copy runs behind the next step's accumulator reads (as a loop of
+          // 16-byte loads and stores by all epilogue threads it was serialised with them: 214 of 590 us on the
+          // 608x608 DarkNet stem).  Columns past the row end and rows past the band are clipped / skipped.
+          if (et == 0) {
+            const int n_rows = min(kT, it.c1 - cs);
+            for (int t = 0; t < n_rows; ++t)
+              tma_store_4d(&tmapOut, rows_addr + static_cast<uint32_t>((cs + t + 1) & (kRowSlots - 1)) * C::kRowBuf, 0,
+                           it.qt * kTileM, cs + t, it.n);
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          }
+        } else if (!p.pool) {
           // copy the rows out: consecutive threads -> consecutive 16 B of the NHWC row
           const int n_rows = min(kT, it.c1 - cs);
           const int per_row = valid_w * kChunks;
@@ -431,6 +455,7 @@ stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     }
   }
 
+  if (threadIdx.x == 64) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");  // the row stores of the last steps
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 0) {
@@ -691,13 +716,26 @@ std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry
                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return "stem: cuTensorMapEncodeTiled (weights) failed";
   }
+  L.tmapOut = L.tmapB;  // unused with the fused max-pool (the pooled row is written with plain stores)
+  if (!pool) {
+    // conv output [N][P][Qw][block_n] (NHWC; pair mode: Qw pixel pairs of 2 x C_out channels), stored one 128-window row
+    // at a time from the swizzled row buffer
+    cuuint64_t dims[4] = {(cuuint64_t)g.block_n, (cuuint64_t)p.Qw, (cuuint64_t)p.P, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)g.block_n * 2, (cuuint64_t)p.Qw * g.block_n * 2, (cuuint64_t)p.P * p.Qw * g.block_n * 2};
+    cuuint32_t box[4] = {(cuuint32_t)g.block_n, (cuuint32_t)kTileM, 1, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = g_encode(&L.tmapOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, out, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, g.block_n == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return "stem: cuTensorMapEncodeTiled (output rows) failed";
+  }
   return "";
 }
 
 cudaError_t stem_rowring_launch(const StemLaunch& L, cudaStream_t st) {
 #define TLXCV_X(BN, RR, SS)                                                                              \
   if (L.block_n == BN && L.p.R == RR && L.p.sv == SS) {                                                  \
-    return launch_pdl(stem_rowring_kernel<BN, RR, SS>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.p); \
+    return launch_pdl(stem_rowring_kernel<BN, RR, SS>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut, L.p); \
   }
   TLXCV_STEM_INSTANCES(TLXCV_X)
 #undef TLXCV_X
