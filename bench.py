@@ -153,8 +153,21 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     return 0
+
+
+_RESULT_FD = None
+
+
+def emit(line):
+    """Write the one JSON line to the process's original stdout (see main())."""
+    data = (json.dumps(line) + "\n").encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
 
 
 def main():
@@ -167,7 +180,12 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
-    os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep stdout to the one JSON line (NCCL prints its version at INFO)
+    # stdout carries exactly ONE line, the JSON result: everything libraries print while the run lasts (NCCL's version
+    # banner at NCCL_DEBUG >= VERSION, torch warnings) goes to stderr; emit() writes the result to the real stdout
+    sys.stdout.flush()
+    global _RESULT_FD
+    _RESULT_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank)
@@ -321,7 +339,7 @@ def main():
             "launches_per_step": plan.num_launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         tdist.destroy_process_group()
     return 0
