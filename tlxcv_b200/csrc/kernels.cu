@@ -303,24 +303,46 @@ __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
   Vec8<T>::store(dst + idx * 8, m);
 }
 
-// global average pool: block per image, thread per 8-channel group, fp32 accumulation in pixel order
+// global average pool: block per image, blockDim = (8-channel groups, kGapSlices pixel slices).  Each thread sums its
+// slice of the pixels in pixel order (fp32), the slices are then added in slice order through shared memory: four times
+// the loads in flight of a thread-per-group kernel, which was latency-bound (49 dependent-issue loads per thread).
+constexpr int kGapSlices = 4;
 template <typename T>
 __global__ void gap_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int HW, int C8) {
+  extern __shared__ float gap_part[];  // [kGapSlices - 1][C8 * 8]
   pdl_wait();
   const int n = blockIdx.x;
   const T* s = src + static_cast<size_t>(n) * HW * C8 * 8;
   const float inv = 1.0f / static_cast<float>(HW);
-  for (int g = threadIdx.x; g < C8; g += blockDim.x) {
+  const int slice = threadIdx.y;
+  const int per = (HW + kGapSlices - 1) / kGapSlices;
+  const int p0 = slice * per, p1 = min(HW, p0 + per);
+  for (int g0 = 0; g0 < C8; g0 += blockDim.x) {
+    const int g = g0 + threadIdx.x;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    for (int p = 0; p < HW; ++p) {
-      float v[8];
-      Vec8<T>::load(s + (static_cast<size_t>(p) * C8 + g) * 8, v);
+    if (g < C8) {
+#pragma unroll 4
+      for (int p = p0; p < p1; ++p) {
+        float v[8];
+        Vec8<T>::load(s + (static_cast<size_t>(p) * C8 + g) * 8, v);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+        for (int i = 0; i < 8; ++i) acc[i] += v[i];
+      }
+      if (slice > 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) gap_part[(static_cast<size_t>(slice - 1) * C8 + g) * 8 + i] = acc[i];
+      }
     }
+    __syncthreads();
+    if (slice == 0 && g < C8) {
+      for (int k = 0; k < kGapSlices - 1; ++k)
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] *= inv;
-    Vec8<T>::store(dst + (static_cast<size_t>(n) * C8 + g) * 8, acc);
+        for (int i = 0; i < 8; ++i) acc[i] += gap_part[(static_cast<size_t>(k) * C8 + g) * 8 + i];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] *= inv;
+      Vec8<T>::store(dst + (static_cast<size_t>(n) * C8 + g) * 8, acc);
+    }
+    __syncthreads();
   }
 }
 
@@ -683,11 +705,14 @@ cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C,
 
 cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st) {
   if (C % 8) return cudaErrorInvalidValue;
-  const int threads = C / 8 >= 256 ? 256 : (C / 8 >= 128 ? 128 : 64);
+  const int tx = C / 8 >= 256 ? 256 : (C / 8 >= 128 ? 128 : 64);
+  const dim3 threads(tx, kGapSlices);
+  const int smem = (kGapSlices - 1) * C * static_cast<int>(sizeof(float));
+  if (smem > 48 * 1024) return cudaErrorInvalidValue;  // C > 4096: not a shape of this path
   if (is_f32)
-    TLXCV_LAUNCH(gap_nhwc_kernel<float>, N, threads, 0, st, static_cast<const float*>(src), static_cast<float*>(dst), HW, C / 8);
+    TLXCV_LAUNCH(gap_nhwc_kernel<float>, N, threads, smem, st, static_cast<const float*>(src), static_cast<float*>(dst), HW, C / 8);
   else
-    TLXCV_LAUNCH(gap_nhwc_kernel<__nv_bfloat16>, N, threads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), HW, C / 8);
+    TLXCV_LAUNCH(gap_nhwc_kernel<__nv_bfloat16>, N, threads, smem, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), HW, C / 8);
   return cudaGetLastError();
 }
 
