@@ -285,11 +285,6 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // DUAL: the tile has TWO accumulators (conv3 of a bottleneck and the block's downsample conv, see the kernel):
 //     y = act1( acc1 * scale + shift  +  acc2 * scale2 + shift2 )
 // the scale/shift buffer then holds [scale | scale2 | shift + shift2] for the tile's BLOCK_N = 128 channels.
-#ifdef TLXCV_EPI_OLD_REFILL  // experiment switch: residual refill right after the store commit, three items ahead
-constexpr bool kOldRefill = true;
-#else
-constexpr bool kOldRefill = false;
-#endif
 template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool DUAL = false>
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
   static_assert(!DUAL || (BLOCK_N == 128 && !RES && !F32), "dual accumulators: 128-wide bf16 tiles without a residual");
@@ -334,7 +329,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   if (RES && lane == 0) {
     if (pf_tile < a.num_tiles) pf_place();
 #pragma unroll
-    for (int k = 0; k < (kOldRefill ? kRing - 1 : kRing == 4 ? 2 : 1); ++k) pf_issue();
+    for (int k = 0; k < (kRing == 4 ? 2 : 1); ++k) pf_issue();
   }
 
   uint32_t it = 0;  // items processed
@@ -416,7 +411,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       if (DUAL) tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + BLOCK_N + chunk * 32,
                                    reinterpret_cast<uint32_t(&)[32]>(v2));
       if (RES) {
-        if (kRing == 4 && !kOldRefill && lane == 0) {
+        if (kRing == 4 && lane == 0) {
           // four slots: [it-1] draining, [it] in use, [it+1] in flight; request item it+2 into the slot item it-2 used.
           // That store was committed a whole item ago, so this wait does not stall (waiting for the store just
           // committed cost ~300 cycles per item), and the request still leads its use by two items.
@@ -443,7 +438,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
           __syncwarp();
           if (lane == 0) release_acc();
         }
-        if (RES && (kRing == 2 || kOldRefill) && lane == 0) pf_issue();
+        if (RES && kRing == 2 && lane == 0) pf_issue();
         continue;
       }
       // fp32 pairs (two adjacent channels per 64-bit register): packed FMA / ADD / MUL halve the fp32 instruction
@@ -563,7 +558,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       if (lane == 0) {
         if (!(a.ablate & 2)) tma_store_2d(a.tmap_out, a.ring + slot * 2048, cbase, m0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-        if (RES && (kRing == 2 || kOldRefill)) {
+        if (RES && kRing == 2) {
           // two slots: refill the slot item it-1 used with item it+1 as soon as its store has read the buffer
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           pf_issue();
