@@ -124,6 +124,43 @@ def cpu_forward_rate(n_images, min_seconds, max_iters=50):
     return n_images / best, cores, len(times), sd, x
 
 
+def gpu_library_rates(device, iters=10):
+    """SURVEY 8(d) "GPU library baseline": the reference's model code (oracle restatement, torch.nn.functional) moved to
+    the GPU as it is - what TL_BACKEND=torch does on a CUDA device - so cuDNN / cuBLAS run every layer unfused.
+    (i) fp32 NCHW eager, the reference's literal configuration; (ii) bf16 channels_last with cuDNN autotune.
+    A reported baseline like cpu_baseline: it never feeds the product path."""
+    import torch
+
+    from oracle import restated
+    from tlxcv_b200 import models
+    from tlxcv_b200.testing import seeded_state_dict, synthetic_images
+
+    out = {}
+    m = models.REGISTRY[MODEL]()
+    sd32 = {k: v.to(device) for k, v in seeded_state_dict(m.state_dict(), MODEL).items()}
+    x32 = synthetic_images(8, SIZE).repeat(PER_GPU_BATCH // 8, 1, 1, 1).to(device)
+    torch.backends.cudnn.benchmark = True
+    for name, sd, x in (("fp32_nchw_eager", sd32, x32),
+                        ("bf16_channels_last_eager",
+                         {k: (v.to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if v.dim() == 4 else
+                              v.to(torch.bfloat16)) for k, v in sd32.items()},
+                         x32.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))):
+        for _ in range(3):
+            restated.forward(MODEL, sd, x)
+        torch.cuda.synchronize(device)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            restated.forward(MODEL, sd, x)
+        e1.record()
+        torch.cuda.synchronize(device)
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"value": PER_GPU_BATCH / ms * 1e3, "unit": UNIT, "ms_per_step": ms}
+    out["what"] = ("oracle restatement of the reference ResNet-50 forward run by torch eager on this GPU (cuDNN/cuBLAS, one "
+                   "library kernel per op, BatchNorm / ReLU / add unfused), bs256, device-resident input")
+    return out
+
+
 def run_reference(args, rank):
     """--impl reference: the reference's CPU path (oracle) on the host cores, same metric and config."""
     if rank != 0:
@@ -177,6 +214,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--gpu-library-baseline", action="store_true",
+                    help="also time the reference's math on cuDNN/cuBLAS (torch eager) on this GPU: adds gpu_library_baseline")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -318,6 +357,10 @@ def main():
                "sample": f"best of {iters} forwards of a {sample}-image sample (oracle restatement of the reference "
                          f"model code, torch CPU fp32, {cores} threads)"}
 
+    lib = None
+    if rank == 0 and world == 1 and args.gpu_library_baseline:
+        lib = gpu_library_rates(device)
+
     if rank == 0:
         total = world * PER_GPU_BATCH
         line = {
@@ -339,6 +382,8 @@ def main():
             "launches_per_step": plan.num_launches,
             "roofline": roof, "cpu_baseline": cpu, "clocks": clocks,
         }
+        if lib is not None:
+            line["gpu_library_baseline"] = lib
         emit(line)
     if world > 1:
         tdist.destroy_process_group()
