@@ -185,65 +185,6 @@ __device__ __forceinline__ void act_inplace(float (&f)[N], int act, float alpha)
   }
 }
 
-// ---- packed fp32x2 / bf16x2 helpers of the epilogue (sm_100: fma/add/mul.f32x2 work on 64-bit register pairs) ----------
-__device__ __forceinline__ unsigned long long pack_u64(uint32_t lo, uint32_t hi) {
-  return static_cast<unsigned long long>(lo) | (static_cast<unsigned long long>(hi) << 32);
-}
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fadd2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long fmul2(unsigned long long a, unsigned long long b) {
-  unsigned long long d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ unsigned long long bf16x2_to_f32x2(uint32_t u) {  // low half -> first float
-  return pack_u64(u << 16, u & 0xffff0000u);
-}
-__device__ __forceinline__ uint32_t pack_pair_bf16(unsigned long long p) {
-  return pack_bf16x2(__uint_as_float(static_cast<uint32_t>(p)), __uint_as_float(static_cast<uint32_t>(p >> 32)));
-}
-__device__ __forceinline__ ulonglong2 ldg_u64x2(const ulonglong2* p) {
-  ulonglong2 r;
-  asm volatile("ld.global.nc.v2.u64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p));
-  return r;
-}
-// activation of an fp32 pair.  LeakyReLU is max(v, alpha * v): exact for 0 <= alpha <= 1, which the planner enforces.
-template <int ACT>
-__device__ __forceinline__ unsigned long long act_pair_f32(unsigned long long p, float alpha) {
-  if (ACT == TLXCV_ACT_NONE) return p;
-  float lo = __uint_as_float(static_cast<uint32_t>(p)), hi = __uint_as_float(static_cast<uint32_t>(p >> 32));
-  if (ACT == TLXCV_ACT_RELU) {
-    lo = fmaxf(lo, 0.0f), hi = fmaxf(hi, 0.0f);
-  } else if (ACT == TLXCV_ACT_RELU6) {
-    lo = fminf(fmaxf(lo, 0.0f), 6.0f), hi = fminf(fmaxf(hi, 0.0f), 6.0f);
-  } else if (ACT == TLXCV_ACT_LEAKY) {
-    const uint32_t al = __float_as_uint(alpha);
-    const unsigned long long m = fmul2(p, pack_u64(al, al));
-    lo = fmaxf(lo, __uint_as_float(static_cast<uint32_t>(m))), hi = fmaxf(hi, __uint_as_float(static_cast<uint32_t>(m >> 32)));
-  }
-  return pack_u64(__float_as_uint(lo), __float_as_uint(hi));
-}
-// fp32 pair -> packed bf16 pair with ReLU / ReLU6 applied after the rounding: cvt.rn.relu clamps in the conversion
-// itself (one instruction per pair), ReLU6 adds a packed min
-template <int ACT>
-__device__ __forceinline__ uint32_t pack_pair_bf16_act(unsigned long long p) {
-  if (ACT != TLXCV_ACT_RELU && ACT != TLXCV_ACT_RELU6) return pack_pair_bf16(p);
-  uint32_t r;
-  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;"
-      : "=r"(r)
-      : "f"(__uint_as_float(static_cast<uint32_t>(p >> 32))), "f"(__uint_as_float(static_cast<uint32_t>(p))));
-  if (ACT == TLXCV_ACT_RELU6) asm("min.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(r), "r"(0x40C040C0u));  // 6.0 | 6.0
-  return r;
-}
-
 // Everything one epilogue warp needs, hoisted out of the loops (kernel parameters live in constant
 // memory; re-reading them through the uniform datapath inside the item loop costs latency).
 struct EpiArgs {

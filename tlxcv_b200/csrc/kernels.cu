@@ -399,15 +399,7 @@ __global__ void dwconv_nhwc_kernel(const T* __restrict__ src, const T* __restric
 //   * math is packed fp32x2 FMA (sm_100 `fma.rn.f32x2`), two channels per instruction;
 //   * the activation switch sits outside the element loops.
 // Adjacent lanes own adjacent channel quads, so each load instruction reads contiguous 256 B runs.
-__device__ __forceinline__ unsigned long long ffma2(unsigned long long a, unsigned long long b, unsigned long long c) {
-  unsigned long long d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ unsigned long long bf16x2_to_f32x2(uint32_t u) {
-  // low half -> first float, high half -> second float (little endian pair in one 64-bit register)
-  return static_cast<unsigned long long>(u << 16) | (static_cast<unsigned long long>(u & 0xffff0000u) << 32);
-}
+// ffma2 / bf16x2_to_f32x2: common.cuh
 __device__ __forceinline__ float2 unpack_f32x2(unsigned long long v) {
   return make_float2(__uint_as_float(static_cast<uint32_t>(v)), __uint_as_float(static_cast<uint32_t>(v >> 32)));
 }

@@ -219,6 +219,8 @@ int compile_stem(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
                                          pool ? out.d.w : 0);
   if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
   StemParams& sp = op.stem.p;
+  if (d.act1 == TLXCV_ACT_LEAKY && !(d.alpha1 >= 0.0f && d.alpha1 <= 1.0f))  // the epilogue evaluates max(v, alpha * v)
+    return fail(ctx, TLXCV_ERR_UNSUPPORTED, "stem conv: LeakyReLU slope outside [0, 1]");
   sp.scale = op.scale, sp.shift = op.shift, sp.act = d.act1, sp.alpha = d.alpha1;
   op.impl = kImplStem;
   const double M = static_cast<double>(N) * g.P * g.Q;

@@ -345,26 +345,36 @@ stem_rowring_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[acc]));
           }
           if (live) {
+            // packed fp32x2 FMA; ReLU / ReLU6 inside the bf16 conversion, LeakyReLU as max(v, alpha v) (slope in [0, 1],
+            // checked by the planner): same values as scale/shift -> activation -> rounding, a third of the instructions
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              float f[8];
-              const float4 s0 = *reinterpret_cast<const float4*>(sc_s + half * 32 + 8 * j);
-              const float4 s1 = *reinterpret_cast<const float4*>(sc_s + half * 32 + 8 * j + 4);
-              const float4 h0 = *reinterpret_cast<const float4*>(sh_s + half * 32 + 8 * j);
-              const float4 h1 = *reinterpret_cast<const float4*>(sh_s + half * 32 + 8 * j + 4);
-              f[0] = fmaf(__uint_as_float(v[8 * j + 0]), s0.x, h0.x);
-              f[1] = fmaf(__uint_as_float(v[8 * j + 1]), s0.y, h0.y);
-              f[2] = fmaf(__uint_as_float(v[8 * j + 2]), s0.z, h0.z);
-              f[3] = fmaf(__uint_as_float(v[8 * j + 3]), s0.w, h0.w);
-              f[4] = fmaf(__uint_as_float(v[8 * j + 4]), s1.x, h1.x);
-              f[5] = fmaf(__uint_as_float(v[8 * j + 5]), s1.y, h1.y);
-              f[6] = fmaf(__uint_as_float(v[8 * j + 6]), s1.z, h1.z);
-              f[7] = fmaf(__uint_as_float(v[8 * j + 7]), s1.w, h1.w);
-              act_regs(f, act, alpha);
+              const ulonglong2 s0 = *reinterpret_cast<const ulonglong2*>(sc_s + half * 32 + 8 * j);
+              const ulonglong2 s1 = *reinterpret_cast<const ulonglong2*>(sc_s + half * 32 + 8 * j + 4);
+              const ulonglong2 h0 = *reinterpret_cast<const ulonglong2*>(sh_s + half * 32 + 8 * j);
+              const ulonglong2 h1 = *reinterpret_cast<const ulonglong2*>(sh_s + half * 32 + 8 * j + 4);
+              unsigned long long q[4];
+              q[0] = ffma2(pack_u64(v[8 * j + 0], v[8 * j + 1]), s0.x, h0.x);
+              q[1] = ffma2(pack_u64(v[8 * j + 2], v[8 * j + 3]), s0.y, h0.y);
+              q[2] = ffma2(pack_u64(v[8 * j + 4], v[8 * j + 5]), s1.x, h1.x);
+              q[3] = ffma2(pack_u64(v[8 * j + 6], v[8 * j + 7]), s1.y, h1.y);
+              uint32_t o[4];
+              if (act == TLXCV_ACT_RELU) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = pack_pair_bf16_act<TLXCV_ACT_RELU>(q[e]);
+              } else if (act == TLXCV_ACT_RELU6) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = pack_pair_bf16_act<TLXCV_ACT_RELU6>(q[e]);
+              } else if (act == TLXCV_ACT_LEAKY) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = pack_pair_bf16(act_pair_f32<TLXCV_ACT_LEAKY>(q[e], alpha));
+              } else {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) o[e] = pack_pair_bf16(q[e]);
+              }
               const uint32_t cidx = static_cast<uint32_t>(half * 4 + j);
               const uint32_t addr = my_row + ((cidx ^ swz) << 4);
-              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(pack_bf16x2(f[0], f[1])),
-                           "r"(pack_bf16x2(f[2], f[3])), "r"(pack_bf16x2(f[4], f[5])), "r"(pack_bf16x2(f[6], f[7]))
+              asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3])
                            : "memory");
             }
           }
