@@ -27,7 +27,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
-from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, synthetic_images  # noqa: E402
+from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, structured_images, synthetic_images  # noqa: E402
 
 # model -> (n_images, image size)
 CASES = {
@@ -40,6 +40,19 @@ CASES = {
     "darknet53_det": (1, 64),
 }
 MANIFEST_ONLY = ["resnet34", "resnet101", "wide_resnet50_2", "resnext50_64x4d"]
+
+# BASELINE.json configurations at their stated size: fixture file -> (model, n_images, image size, subsample).
+# Images are testing.structured_images (image i depends on (seed, i) only), so they are the FIRST n images of the full batch the GPU test feeds
+# (ResNet-50: the whole bs256 batch; MobileNetV2 bs512 / ResNeXt-50 bs256: the first 64 images; DarkNet-53 bs64 at
+# 608x608: the first 2 images).  DarkNet's three feature maps are 20 MB per image pair: the fixture keeps a strided
+# subsample ([:, ::4, ::3, ::3]) plus float64 sum / abs-sum checksums of the full maps.
+FULL_SIZE = {
+    "resnet50_bs256": ("resnet50", 256, 224, False),
+    "mobilenet_v2_bs64": ("mobilenet_v2", 64, 224, False),
+    "resnext50_32x4d_bs64": ("resnext50_32x4d", 64, 224, False),
+    "darknet53_det_608": ("darknet53_det", 2, 608, True),
+}
+SUB = (slice(None), slice(None, None, 4), slice(None, None, 3), slice(None, None, 3))
 
 
 def main():
@@ -69,6 +82,30 @@ def main():
             **arrays,
         )
         print(name, [tuple(o.shape) for o in outs], "std", float(outs[0].std()))
+    for fname, (name, n, size, sub) in FULL_SIZE.items():
+        model = ref_loader.build(name)
+        sd = seeded_state_dict(model.state_dict(), name)
+        model.load_state_dict(sd)
+        model.set_eval()
+        x = structured_images(n, size)
+        with torch.no_grad():
+            y = model({"images": x}) if name == "darknet53_det" else model(x)
+        outs = y if isinstance(y, (list, tuple)) else [y]
+        arrays = {}
+        for i, o in enumerate(outs):
+            arrays[f"out{i}"] = (o[SUB] if sub else o).contiguous().numpy()
+            if sub:
+                arrays[f"sum{i}"] = np.float64(o.double().sum().item())
+                arrays[f"abssum{i}"] = np.float64(o.double().abs().sum().item())
+                arrays[f"shape{i}"] = np.array(o.shape, dtype=np.int64)
+        np.savez_compressed(
+            os.path.join(out_dir, f"{fname}.npz"),
+            model=np.array(name), n=np.int64(n), size=np.int64(size), subsampled=np.int64(1 if sub else 0),
+            weight_digest=np.array(state_dict_digest(sd)),
+            input_digest=np.array(state_dict_digest({"x": x})),
+            **arrays,
+        )
+        print(fname, [tuple(o.shape) for o in outs], "std", float(outs[0].std()))
     with open(os.path.join(out_dir, "manifests.json"), "w") as f:
         json.dump(manifests, f)
     print("wrote", out_dir)

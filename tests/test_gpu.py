@@ -392,9 +392,10 @@ def test_classifier_bf16_vs_golden_reference_outputs(name):
     top2 = r.topk(2, dim=1).values
     margin = top2[:, 0] - top2[:, 1]
     assert err <= 1e-2, f"{name}: max-abs logit error {err:.3e} (logit std {float(r.std()):.3f})"
-    # identical top-1 wherever the reference's own decision margin exceeds twice the error bound
+    # identical top-1; a difference is only possible (and tolerated) where the reference's own margin is within twice
+    # the measured error
     agree = y.argmax(1) == r.argmax(1)
-    assert bool((agree | (margin < 2e-2)).all())
+    assert bool((agree | (margin <= 2 * err)).all())
 
 
 @pytest.mark.parametrize("name", ["resnet50", "mobilenet_v2", "resnext50_32x4d"])
@@ -451,29 +452,79 @@ def test_resnet50_bs256_batch_invariance_and_predict():
     assert pred.dtype == torch.int64 and torch.equal(pred, full.argmax(1))
 
 
-@pytest.mark.parametrize("name,batch,size,uniq", [("mobilenet_v2", 512, 224, 32), ("resnext50_32x4d", 256, 224, 32),
-                                                  ("darknet53_det", 64, 608, 4)])
-def test_full_size_configs_batch_invariance(name, batch, size, uniq):
-    """The other BASELINE.json configurations at their full sizes (MobileNetV2 bs512, ResNeXt-50 32x4d bs256, DarkNet-53
-    bs64 at 608x608): a batch made of `uniq` distinct images repeated must give bit-identical results for every copy
-    (the kernels picked for the full-size plan treat images independently), and agree with the `uniq`-image plan that the
-    oracle tests pin (other tile shapes there: same math, other summation order)."""
+@pytest.mark.parametrize("fname,batch", [("resnet50_bs256", 256), ("mobilenet_v2_bs64", 512), ("resnext50_32x4d_bs64", 256)])
+def test_full_size_classifier_vs_reference_golden(fname, batch):
+    """BASELINE.json configurations at their stated batch against the outputs of the reference's own model files
+    (tests/golden/make_golden.py FULL_SIZE): ResNet-50 all 256 images of the bs256 plan, MobileNetV2 bs512 / ResNeXt-50
+    bs256 their first 64 images.  Bar (north_star): max-abs logit error <= 1e-2 and identical top-1; a top-1 difference is
+    only tolerated where the reference's own top-1/top-2 margin is within twice the measured error (reported, not hidden).
+    Images are all distinct (testing.structured_images).  Batch invariance rides along: the reversed batch must give the
+    reversed logits bit for bit."""
     from tlxcv_b200 import models
-    from tlxcv_b200.testing import seeded_state_dict, synthetic_images
+    from tlxcv_b200.testing import parity_stats, seeded_state_dict, structured_images
 
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"{fname}.npz"))
+    name, n = str(g["model"]), int(g["n"])
+    ref = torch.from_numpy(g["out0"])
     m = models.REGISTRY[name]()
     m.load_state_dict(seeded_state_dict(m.state_dict(), name))
     m = m.cuda().set_eval()
-    small = synthetic_images(uniq, size, seed=11).cuda()
-    x = small.repeat(batch // uniq, 1, 1, 1).contiguous()
-    as_list = lambda y: list(y) if isinstance(y, (list, tuple)) else [y]
-    full = as_list(m({"images": x}) if name == "darknet53_det" else m(x))
-    part = as_list(m({"images": small}) if name == "darknet53_det" else m(small))
-    for f, q in zip(full, part):
-        assert f.shape[0] == batch and bool(torch.isfinite(f).all())
-        assert torch.equal(f[:uniq], f[uniq:2 * uniq]) and torch.equal(f[:uniq], f[batch - uniq:])
-        scale = max(1.0, float(q.abs().max()))
-        assert float((f[:uniq] - q).abs().max()) <= 2.0 ** -6 * scale
+    x = structured_images(batch, 224).cuda()
+    y = m(x)
+    assert y.shape == (batch, 1000) and bool(torch.isfinite(y).all())
+    st = parity_stats(y[:n], ref)
+    print(f"\n{fname}: {st}")
+    assert st["max_abs"] <= 1e-2, st
+    assert st["top1_unexplained"] == 0, st
+    # random-init logits have near-ties (ResNet-50: 75 of 256 reference margins are below 2e-2, the smallest 1.8e-4):
+    # those may flip under bf16 rounding, and only those (checked above); everything else must agree
+    assert st["top1_agree"] >= int(0.9 * n), st
+    y_rev = m(x.flip(0).contiguous())
+    assert torch.equal(y_rev.flip(0), y)
+    if fname == "resnet50_bs256":
+        # fp32 validation mode on the same 256 images: <= 1e-4, and top-1 identical wherever the margin exceeds 2e-4
+        from tlxcv_b200 import runtime
+        plan32, _, flat = runtime.get_plan(m, (x,), {}, precision=runtime.PREC_F32)
+        st32 = parity_stats(plan32.run(flat, graph=False)[0], ref)
+        print(f"{fname} fp32 validation mode: {st32}")
+        assert st32["max_abs"] <= 1e-4 and st32["top1_unexplained"] == 0 and st32["top1_agree"] >= n - 2, st32
+
+
+def test_darknet53_608_bs64_vs_oracle_and_reference_golden():
+    """DarkNet-53 detection backbone at BASELINE's size (bs64, 608x608; detection/backbones/darknet.py:299-312): the first two
+    images of the bs64 plan against the CPU oracle's full feature maps and against the fixture minted by the reference's
+    own file (strided subsample + checksums).  This plan uses tilings the 64x64 golden cannot reach (slab_c32 with three
+    column segments, the pairs stem with several column tiles, CTA pairs on >= 256 M tiles)."""
+    from oracle import restated
+    from tlxcv_b200 import models
+    from tlxcv_b200.testing import seeded_state_dict, structured_images
+
+    g = np.load(os.path.join(ROOT, "tests", "golden", "darknet53_det_608.npz"))
+    n = int(g["n"])
+    m = models.DarkNet()
+    sd = seeded_state_dict(m.state_dict(), "darknet53_det")
+    m.load_state_dict(sd)
+    m = m.cuda().set_eval()
+    x = structured_images(64, 608)
+    feats = m({"images": x.cuda()})
+    assert [tuple(f.shape) for f in feats] == [(64, 256, 76, 76), (64, 512, 38, 38), (64, 1024, 19, 19)]
+    refs = restated.forward("darknet53_det", sd, {"images": x[:n]})
+    sub = (slice(None), slice(None, None, 4), slice(None, None, 3), slice(None, None, 3))
+    for i, (f, r) in enumerate(zip(feats, refs)):
+        assert bool(torch.isfinite(f).all())
+        o = f[:n].cpu()
+        scale = float(r.abs().max())
+        rel_max = float((o - r).abs().max()) / scale
+        rel_rms = float((o - r).pow(2).mean().sqrt()) / float(r.pow(2).mean().sqrt())
+        print(f"\ndarknet53@608 map {i}: max-abs/scale {rel_max:.4f}, rms rel {rel_rms:.5f}, scale {scale:.2f}")
+        assert rel_max <= 0.03 and rel_rms <= 0.01, (i, rel_max, rel_rms)
+        gold = torch.from_numpy(g[f"out{i}"])
+        assert float((o[sub] - gold).abs().max()) <= 0.03 * scale
+        assert abs(float(o.double().sum()) - float(g[f"sum{i}"])) <= 0.01 * float(g[f"abssum{i}"])
+    # images are independent: the reversed batch gives the reversed maps, bit for bit
+    rev = m({"images": x.flip(0).contiguous().cuda()})
+    for f, q in zip(feats, rev):
+        assert torch.equal(q[-2:].flip(0), f[:2])
 
 
 def test_leaky_relu_slope_outside_unit_interval_is_refused():
@@ -561,3 +612,73 @@ def test_host_pipeline_matches_device_path():
     pipe.synchronize()
     for xi, oi in zip(xs, outs):
         assert torch.equal(oi, m(xi.cuda()).cpu())
+
+
+def test_plan_run_host_c_abi_call():
+    """tlxcv_plan_run_host (include/tlxcv_b200.h): pinned host buffers in / out, H2D + forward + D2H on one stream."""
+    from tlxcv_b200 import models, runtime
+    from tlxcv_b200.testing import seeded_state_dict, structured_images
+
+    m = models.resnet18()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), "resnet18"))
+    m = m.cuda().set_eval()
+    x = structured_images(3, 96).pin_memory()
+    plan, _, _ = runtime.get_plan(m, (x.cuda(),), {})
+    out = torch.full((3, 1000), float("nan")).pin_memory()
+    for _ in range(2):          # second call: staging buffers and (from the second use of the pointer set) the graph are reused
+        plan.run_host([x], [out])
+        torch.cuda.synchronize()
+        assert torch.equal(out, m(x.cuda()).cpu())
+
+
+def test_fresh_output_buffers_do_not_recapture_and_repeated_pointers_get_a_whole_graph():
+    """plan_run with graphs: a pointer set seen for the first time runs in segment mode (workspace-only runs of ops are
+    captured once, independent of the caller's buffers); a pointer set that comes back is promoted to a whole-forward
+    graph.  All three routes (stream launch, segments, whole graph) must give the same bits."""
+    from tlxcv_b200 import models, runtime
+    from tlxcv_b200.testing import seeded_state_dict, structured_images
+
+    m = models.resnet18()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), "resnet18"))
+    m = m.cuda().set_eval()
+    x = structured_images(2, 64).cuda()
+    plan, _, flat = runtime.get_plan(m, (x,), {})
+    want = plan.run(flat, graph=False)[0].clone()
+    outs = [plan.run(flat, graph=True)[0] for _ in range(12)]          # 12 fresh output tensors: 12 new pointer sets
+    assert all(torch.equal(o, want) for o in outs)
+    fixed = plan.alloc_outputs()
+    for _ in range(3):                                                  # segments, then capture, then replay
+        plan.run(flat, fixed, graph=True)
+        assert torch.equal(fixed[0], want)
+
+
+@pytest.mark.parametrize("name,classes", [("resnet18", 10), ("mobilenet_v1", 10), ("resnext50_32x4d", 10), ("resnet18", 37)])
+def test_heads_with_class_counts_that_are_not_multiples_of_eight(name, classes):
+    """The reference's predict demos build resnet18 / MobileNetV1 / resnext50_32x4d with num_classes=10
+    (demo/image_classification/predict*.py): the fp32 logits of any class count leave through the tcgen05 Linear."""
+    from oracle import restated
+    from tlxcv_b200 import models
+    from tlxcv_b200.testing import parity_stats, seeded_state_dict, structured_images
+
+    m = models.REGISTRY[name](num_classes=classes)
+    sd = seeded_state_dict(m.state_dict(), name)
+    m.load_state_dict(sd)
+    m = m.cuda().set_eval()
+    x = structured_images(3, 64 if name == "resnet18" else 96)
+    y = m(x.cuda()).cpu()
+    ref = restated.forward(name, sd, x)
+    assert y.shape == (3, classes) == ref.shape
+    st = parity_stats(y, ref)
+    assert st["max_abs"] <= 1e-2 and st["top1_unexplained"] == 0, st
+
+
+def test_returned_map_with_291_channels_bias_only_head():
+    """YOLOv3's output convs (detection/yolov3.py:306-325: 1x1, bias, no BN, 3 x (92 + 5) = 291 channels): a returned map
+    may have any channel count; its rows are stored padded to 8 channels and the export drops the padding."""
+    err, tol, kernels, finite = _layer_case(n=2, cin=256, hw=19, cout=291, k=1, stride=1, pad=0, bn=False, bias=True, seed=5)
+    assert any(k.startswith("conv_tcgen05_tiled") for k in kernels), kernels
+    assert finite and err <= tol, (err, tol)
+    err, tol, kernels, finite = _layer_case(n=1, cin=64, hw=9, cout=44, k=3, stride=1, pad=1, bn=True, act="leaky", seed=6)
+    assert finite and err <= tol, (err, tol)
+    err, tol, _, finite = _layer_case(n=1, cin=64, hw=9, cout=44, k=1, stride=1, pad=0, bias=True, bn=False, prec="f32", seed=7)
+    assert finite and err <= tol, (err, tol)

@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from oracle import ref_loader, restated, tlx_compat
-from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, synthetic_images
+from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, structured_images, synthetic_images
 
 GOLDEN = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls", "darknet53_det"]
 # fixtures were minted with oneDNN on the build container's CPU; another CPU may pick other conv kernels
@@ -40,6 +40,36 @@ def test_restated_matches_golden(name, golden_dir, manifests):
         assert float((a - b).abs().max()) <= ATOL * max(1.0, float(b.abs().max()))
     if name != "darknet53_det":
         assert torch.equal(ys[0].argmax(1), outs[0].argmax(1))
+
+
+FULL_SIZE = ["resnet50_bs256", "mobilenet_v2_bs64", "resnext50_32x4d_bs64", "darknet53_det_608"]
+SUB = (slice(None), slice(None, None, 4), slice(None, None, 3), slice(None, None, 3))
+
+
+@pytest.mark.parametrize("fname", FULL_SIZE)
+def test_restated_matches_full_size_golden(fname, golden_dir, manifests):
+    """The BASELINE.json configurations at their stated size (ResNet-50: the whole bs256 batch; DarkNet-53 at 608x608):
+    fixtures minted by the reference's own files on testing.structured_images."""
+    g = np.load(os.path.join(golden_dir, f"{fname}.npz"))
+    name, n, size, sub = str(g["model"]), int(g["n"]), int(g["size"]), bool(int(g["subsampled"]))
+    sd = seeded_state_dict(dict(manifests[name]), name)
+    assert state_dict_digest(sd) == str(g["weight_digest"])
+    x = structured_images(n, size)
+    assert state_dict_digest({"x": x}) == str(g["input_digest"])
+    y = restated.forward(name, sd, {"images": x} if name == "darknet53_det" else x)
+    ys = y if isinstance(y, list) else [y]
+    for i, a in enumerate(ys):
+        b = torch.from_numpy(g[f"out{i}"])
+        scale = max(1.0, float(b.abs().max()))
+        if sub:
+            assert tuple(a.shape) == tuple(int(v) for v in g[f"shape{i}"])
+            assert float((a[SUB] - b).abs().max()) <= ATOL * scale
+            assert abs(float(a.double().sum()) - float(g[f"sum{i}"])) <= 1e-6 * float(g[f"abssum{i}"])
+            assert abs(float(a.double().abs().sum()) - float(g[f"abssum{i}"])) <= 1e-6 * float(g[f"abssum{i}"])
+        else:
+            assert float((a - b).abs().max()) <= ATOL * scale
+            assert torch.equal(a.argmax(1), b.argmax(1))
+            assert len(set(b.argmax(1).tolist())) >= (3 if n >= 256 else 1)      # the images do differ
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")

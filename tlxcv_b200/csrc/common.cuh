@@ -9,6 +9,7 @@
 #include <stdlib.h>
 
 #include "../../include/tlxcv_b200.h"
+#include "env.h"
 
 namespace tlxcv {
 
@@ -103,7 +104,7 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 inline bool pdl_enabled() {
-  static const bool on = getenv("TLXCV_NO_PDL") == nullptr;
+  static const bool on = tuning_env("TLXCV_NO_PDL") == nullptr;
   return on;
 }
 

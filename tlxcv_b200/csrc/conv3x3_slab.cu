@@ -475,13 +475,13 @@ EncodeTiledFnB g_encode_b = nullptr;
 }  // namespace
 
 bool conv3x3_slab_supported(int Cin, int Cout, int H, int W, int R, int S, int stride, int pad, int dil, int groups) {
-  if (getenv("TLXCV_NO_SLAB")) return false;
+  if (tuning_env("TLXCV_NO_SLAB")) return false;
   if (R != 3 || S != 3 || stride != 1 || pad != 1 || dil != 1 || W < 8 || H < 1) return false;
   if (groups == 1) return (Cin == 64 || Cin == 32) && Cout == 64;
   // grouped: channels-per-group divides 64 and nothing crosses a 64-channel block.  Small maps stay on the im2col
   // path of conv_tcgen05.cu (measured: 14x14 x 512 channels 0.107 ms here against 0.077 ms there).
   const int cpg = Cin / groups;
-  return Cin == Cout && Cin % 64 == 0 && cpg * groups == Cin && 64 % cpg == 0 && (W >= 20 || getenv("TLXCV_FORCE_SLAB"));
+  return Cin == Cout && Cin % 64 == 0 && cpg * groups == Cin && 64 % cpg == 0 && (W >= 20 || tuning_env("TLXCV_FORCE_SLAB"));
 }
 
 cudaError_t conv3x3_slab_set_attributes() {
@@ -512,7 +512,7 @@ std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat1
   p.ng = 1 + (2 + p.T - 1) / p.T;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.residual = static_cast<const __nv_bfloat16*>(residual);
-  if (const char* e = getenv("TLXCV_DEBUG_ABLATE_SLAB")) p.ablate = atoi(e);  // timing experiments only: results are wrong
+  if (const char* e = debug_env("TLXCV_DEBUG_ABLATE_SLAB")) p.ablate = atoi(e);  // timing experiments only: results are wrong
   if (Ktot != 9 * CB) return "slab conv: packed weight K does not match 9 taps x channel block";
   const int pix = 2 * CB, row_bytes = Wp * pix;
   const int stage = (p.T * p.Ws * kBlockN * 2 + 127) / 128 * 128;
@@ -536,7 +536,7 @@ std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat1
     const long long cost = per_cta * (steps * 10 + 6);
     if (best < 0 || cost < best) best = cost, p.bands = bands, p.band_rows = rows;
   }
-  if (const char* e = getenv("TLXCV_DEBUG_SLAB_BANDS")) {  // A/B timing only
+  if (const char* e = tuning_env("TLXCV_DEBUG_SLAB_BANDS")) {  // A/B timing only
     const int bands = std::max(1, std::min(H, atoi(e)));
     p.band_rows = (H + bands - 1) / bands;
     p.bands = (H + p.band_rows - 1) / p.band_rows;
@@ -570,7 +570,7 @@ std::string conv3x3_slab_prepare(SlabLaunch& L, int sm_count, const __nv_bfloat1
 }
 
 cudaError_t conv3x3_slab_launch(const SlabLaunch& L, cudaStream_t st) {
-  static const char* trace_path = getenv("TLXCV_DEBUG_TRACE_SLAB");  // debugging: dump CTA 0's pipeline timeline
+  static const char* trace_path = debug_env("TLXCV_DEBUG_TRACE_SLAB");  // debugging: dump CTA 0's pipeline timeline
   if (trace_path != nullptr) {
     static unsigned long long* dbuf = nullptr;
     if (!dbuf) cudaMalloc(&dbuf, 3 * kTraceLen * sizeof(unsigned long long));

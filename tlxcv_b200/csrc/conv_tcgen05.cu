@@ -451,9 +451,17 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         const int gr = m0 + lane;
         if (gr < a.M) {
           float* dst = a.out_f32 + static_cast<size_t>(gr) * a.Cout + cbase;
+          if ((a.Cout & 3) == 0) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            if (cbase + 4 * j < a.Cout) reinterpret_cast<ulonglong2*>(dst)[j] = make_ulonglong2(pr[2 * j], pr[2 * j + 1]);
+            for (int j = 0; j < 8; ++j)
+              if (cbase + 4 * j < a.Cout) reinterpret_cast<ulonglong2*>(dst)[j] = make_ulonglong2(pr[2 * j], pr[2 * j + 1]);
+          } else {  // class counts that are not a multiple of 4 (num_classes=10 heads): rows are not 16-byte aligned
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              if (cbase + 2 * j < a.Cout) dst[2 * j] = __uint_as_float(static_cast<uint32_t>(pr[j]));
+              if (cbase + 2 * j + 1 < a.Cout) dst[2 * j + 1] = __uint_as_float(static_cast<uint32_t>(pr[j] >> 32));
+            }
+          }
         }
         continue;
       }
@@ -998,8 +1006,8 @@ template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
   // debugging: dump CTA 0's timeline of conv launch number TLXCV_DEBUG_TRACE_CONV_INDEX (default: every launch, so the
   // file holds the last one)
-  static const char* trace_path = getenv("TLXCV_DEBUG_TRACE_CONV");
-  static const int trace_index = getenv("TLXCV_DEBUG_TRACE_CONV_INDEX") ? atoi(getenv("TLXCV_DEBUG_TRACE_CONV_INDEX")) : -1;
+  static const char* trace_path = debug_env("TLXCV_DEBUG_TRACE_CONV");
+  static const int trace_index = debug_env("TLXCV_DEBUG_TRACE_CONV_INDEX") ? atoi(debug_env("TLXCV_DEBUG_TRACE_CONV_INDEX")) : -1;
   static int& launch_counter = conv_launch_counter();
   const int my_index = launch_counter++;
   if (trace_path != nullptr && (trace_index < 0 || trace_index == my_index)) {
@@ -1053,7 +1061,7 @@ int stages_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
 // stores, TMA store reads, scale/shift broadcasts next to the MMA operand reads) and the per-chunk proxy fence, not by
 // the number of warps issuing.
 void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_bf16, bool two = false) {
-  static const int force = getenv("TLXCV_DEBUG_EPI_WARPS") ? atoi(getenv("TLXCV_DEBUG_EPI_WARPS")) : 0;
+  static const int force = tuning_env("TLXCV_DEBUG_EPI_WARPS") ? atoi(tuning_env("TLXCV_DEBUG_EPI_WARPS")) : 0;
   const bool light = p.num_kb <= 8;
   p.epi_warps = 8;
   if (force == 8 || (force == 16 && kEpiWarps >= 16)) p.epi_warps = force;
@@ -1064,10 +1072,10 @@ void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_b
   // scale/shift: one smem buffer filled once (single N tile); two buffers refreshed per tile by the epilogue
   // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
   p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps, two) == stages_for(block_n, p.ring, 1, p.epi_warps, two)) ? 2 : 1;
-  if (const char* e = getenv("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
-  if (const char* e = getenv("TLXCV_DEBUG_RING")) p.ring = (atoi(e) == 4 && out_bf16) ? 4 : 2;  // A/B timing only
+  if (const char* e = tuning_env("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
+  if (const char* e = tuning_env("TLXCV_DEBUG_RING")) p.ring = (atoi(e) == 4 && out_bf16) ? 4 : 2;  // A/B timing only
   p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
-  if (const char* e = getenv("TLXCV_DEBUG_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));  // A/B timing only
+  if (const char* e = tuning_env("TLXCV_DEBUG_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));  // A/B timing only
 }
 
 }  // namespace
@@ -1106,7 +1114,8 @@ cudaError_t tc_conv_set_attributes() {
 
 std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
                             int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
-                            int pad, int dil, int groups, int force_block_n, void* out_bf16, const void* residual_bf16) {
+                            int pad, int dil, int groups, int force_block_n, void* out_bf16, int Cout_storage,
+                            const void* residual_bf16) {
   std::string err = load_driver_entry_points();
   if (!err.empty()) return err;
   memset(&L, 0, sizeof L);
@@ -1119,7 +1128,10 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   p.M = static_cast<int>(M);
   p.Cout = Cout;
   p.S = S, p.R = R, p.P = P, p.Q = Q, p.H = H, p.W = W, p.stride = stride, p.pad = pad, p.dil = dil;
-  if (Cout % 8) return "conv: C_out must be a multiple of 8 on the tensor-core path";
+  // bf16 maps: rows padded to a multiple of 8 channels (16 bytes: the TMA store's global stride unit), the store clips at
+  // C_out; fp32 outputs (logits of any class count) are written with direct stores
+  if (out_bf16 != nullptr && (Cout_storage % 8 || Cout_storage < Cout)) return "conv: output rows must be padded to a multiple of 8 channels";
+  if (residual_bf16 != nullptr && Cout_storage != Cout) return "conv: a residual needs an unpadded output";
 
   int block_n;
   if (mode == kModeGatherC4) {
@@ -1170,7 +1182,7 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   L.threads = mode == kModeGatherC4 ? kThreadsGather : kThreadsBase;
   // residual layers and short-K (HBM / epilogue bound) layers get the deep store ring; long-K
   // (MMA bound) layers trade it for one more operand stage
-  if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only: results are wrong
+  if (const char* e = debug_env("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only: results are wrong
   // CTA pairs (cta_group::2) for the 256-wide layers with enough K per tile to be bound by MMA / L2 operand traffic
   // rather than by the epilogue; TLXCV_DEBUG_2SM=0/1 forces it off / on where legal
   // (measured on B200, bs256: 14x14 maps 1024->256 35.8 -> 33.8 us, 512->1024 58.4 -> 54.3 us; 7x7 maps with their 98
@@ -1179,7 +1191,7 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // 128-wide pairs measured: no gain.  Few M tiles (7x7 maps: 98) pair only with a long K loop: bs256 512->512 3x3
   // 63.5 -> 57.3 us, 2048->512 33.8 -> 31.7 us, but 512->2048 + residual (8 K blocks) 38.9 -> 43.9 us.
   bool two = pairable && block_n == 256 && ((p.num_kb >= 8 && p.m_tiles >= 256) || (p.num_kb >= 16 && p.m_tiles >= 64));
-  if (const char* e = getenv("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && p.m_tiles >= 2;
+  if (const char* e = tuning_env("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && p.m_tiles >= 2;
   L.two = two ? 1 : 0;
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two);
   L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
@@ -1202,7 +1214,7 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // output [M][Cout] bf16 written by per-warp TMA stores of 32 rows x 32 channels (64 B rows, SWIZZLE_64B);
   // fp32 outputs (logits) are written with direct stores and leave the map unused
   if (out_bf16)
-    err = encode_2d(&L.tmapOut, out_bf16, Cout, p.M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    err = encode_2d(&L.tmapOut, out_bf16, Cout, p.M, static_cast<uint64_t>(Cout_storage) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
   else
     L.tmapOut = L.tmapB;
   if (!err.empty()) return err;
@@ -1239,7 +1251,7 @@ std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloa
   p.m_tiles = (M + kBlockM - 1) / kBlockM;
   p.n_tiles = (Cout + block_n - 1) / block_n;
   L.mode = kModeTiled, L.block_n = block_n, L.dual = 1, L.threads = kThreadsBase;
-  if (const char* e = getenv("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);
+  if (const char* e = debug_env("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);
   choose_epilogue(p, block_n, false, true);
   if (p.sc_bufs != 2 && stages_for(block_n, p.ring, 2, p.epi_warps) >= 2) {  // the dual epilogue reads four vectors: keep them in smem
     p.sc_bufs = 2;

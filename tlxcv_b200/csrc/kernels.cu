@@ -207,15 +207,15 @@ __global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __rest
 }
 
 template <typename T>
-__global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int HW) {
+__global__ void export_nchw_tile_kernel(const T* __restrict__ src, float* __restrict__ dst, int C, int Cs, int HW) {
   pdl_wait();
   __shared__ float tile[32][33];
   const int n = blockIdx.z, c0 = blockIdx.y * 32, p0 = blockIdx.x * 32;
-  const T* s = src + static_cast<size_t>(n) * HW * C;
+  const T* s = src + static_cast<size_t>(n) * HW * Cs;
   float* d = dst + static_cast<size_t>(n) * C * HW;
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
     const int p = p0 + i, c = c0 + threadIdx.x;
-    tile[i][threadIdx.x] = (p < HW && c < C) ? to_f32(s[static_cast<size_t>(p) * C + c]) : 0.0f;
+    tile[i][threadIdx.x] = (p < HW && c < C) ? to_f32(s[static_cast<size_t>(p) * Cs + c]) : 0.0f;
   }
   __syncthreads();
   for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -665,19 +665,19 @@ cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, con
   return cudaGetLastError();
 }
 
-cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W, int is_f32, cudaStream_t st) {
+cudaError_t export_nchw(const void* src, float* dst, int N, int C, int Cs, int H, int W, int is_f32, cudaStream_t st) {
   const int HW = H * W;
   dim3 grid((HW + 31) / 32, (C + 31) / 32, N), block(32, 8);
   if (is_f32) {
-    TLXCV_LAUNCH(export_nchw_tile_kernel<float>, grid, block, 0, st, static_cast<const float*>(src), dst, C, HW);
-  } else if (C % 8 == 0) {
+    TLXCV_LAUNCH(export_nchw_tile_kernel<float>, grid, block, 0, st, static_cast<const float*>(src), dst, C, Cs, HW);
+  } else if (C % 8 == 0 && Cs == C) {
     dim3 grid64((HW + 63) / 64, (C + 63) / 64, N);
     if (HW % 4 == 0 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0)
       TLXCV_LAUNCH(export_nchw_bf16_64_kernel<true>, grid64, 256, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
     else
       TLXCV_LAUNCH(export_nchw_bf16_64_kernel<false>, grid64, 256, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
   } else {
-    TLXCV_LAUNCH(export_nchw_tile_kernel<__nv_bfloat16>, grid, block, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, HW);
+    TLXCV_LAUNCH(export_nchw_tile_kernel<__nv_bfloat16>, grid, block, 0, st, static_cast<const __nv_bfloat16*>(src), dst, C, Cs, HW);
   }
   return cudaGetLastError();
 }
@@ -823,7 +823,7 @@ cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const flo
     const __nv_bfloat16* wp = static_cast<const __nv_bfloat16*>(w_rsc);
     const __nv_bfloat16* rp = static_cast<const __nv_bfloat16*>(residual);
     __nv_bfloat16* y = static_cast<__nv_bfloat16*>(dst);
-    if (rp == nullptr && N <= 65535 && !getenv("TLXCV_NO_DW_FAST")) {
+    if (rp == nullptr && N <= 65535 && !tuning_env("TLXCV_NO_DW_FAST")) {
 #define TLXCV_X(CC)                                                                                                   \
   if (C == CC)                                                                                                        \
     return stride == 1 ? launch_dw_c<1, CC>(x, wp, y, scale, shift, N, H, W, P, Q, act1, alpha1, st)                  \

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "../../include/tlxcv_b200.h"
+#include "env.h"
 
 namespace tlxcv {
 
@@ -65,7 +66,7 @@ struct TcConvLaunch {
 // Encodes the TMA descriptors and picks tile shape; returns an empty string or an error message.
 std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
                             int Cin_storage, const __nv_bfloat16* packed_w, int Ktot, int Cout, int R, int S, int stride,
-                            int pad, int dil, int groups, int force_block_n, void* out_bf16, const void* residual_bf16);
+                            int pad, int dil, int groups, int force_block_n, void* out_bf16, int Cout_storage, const void* residual_bf16);
 // out = act( A1[M][K1] * W1^T * scale + shift  +  conv1x1_stride(A2) * W2^T * scale2 + shift2 ): two accumulators per tile
 std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloat16* a1, int M, int K1,
                                  const __nv_bfloat16* w1, const __nv_bfloat16* a2, int N, int H2, int W2, int C2, int stride2,
@@ -179,7 +180,8 @@ cudaError_t fold_bn(float* scale, float* shift, const float* gamma, const float*
 
 // ---- memory-bound kernels (T = __nv_bfloat16 or float, is_f32 selects) -------------------------
 cudaError_t import_nchw(const float* src, void* dst, int N, int C, int H, int W, int Cs, int is_f32, cudaStream_t st);
-cudaError_t export_nchw(const void* src, float* dst, int N, int C, int H, int W, int is_f32, cudaStream_t st);
+// src rows hold Cs >= C channels (Cs == C except for maps whose channel count is not a multiple of 8)
+cudaError_t export_nchw(const void* src, float* dst, int N, int C, int Cs, int H, int W, int is_f32, cudaStream_t st);
 // NHWC uint8 (C <= 4) -> [N][H][Wp][4] activations, (x - mean[c]) / std[c]; Wp == W, pad_l == 0 for the dense layout
 cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, const float* stdv, int N, int C, int H, int W,
                            int Wp, int pad_l, int is_f32, cudaStream_t st);

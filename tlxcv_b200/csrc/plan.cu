@@ -7,6 +7,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -74,6 +75,18 @@ struct tlxcv_plan {
   // CUDA graph cache keyed by the external pointers (same pointers => replay); a few entries so that
   // double-buffered callers do not re-capture every step
   std::vector<std::pair<std::vector<const void*>, cudaGraphExec_t>> graphs;
+  std::mutex graphs_mu;  // ctypes releases the GIL around plan_run: two host threads may look up / capture at once
+  // A pointer set seen for the first time runs in SEGMENTS instead: the runs of ops that touch only the plan's own
+  // workspace are captured ONCE (independent of the caller's pointers) and the few ops that read an external input or
+  // write an external output are launched directly around them, in op order.  A caller that allocates fresh outputs on
+  // every forward therefore never re-captures; a pointer set that comes back is promoted to a whole-forward graph.
+  struct Segment {
+    int begin, end;
+    bool graphable;
+    cudaGraphExec_t exec;
+  };
+  std::vector<Segment> segments;
+  std::vector<std::vector<const void*>> seen_keys;  // pointer sets run once in segment mode (bounded)
   // host-run staging
   std::vector<void*> stage_in, stage_out;
 };
@@ -112,6 +125,19 @@ size_t dtype_size(const tlxcv_plan* p, int dt) {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Makes `device` current for the scope and restores the caller's device afterwards: a process with several GPUs (or a
+// plan destroyed from a garbage collector at an arbitrary moment) must not find its current device changed.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
 
 // first-fit arena with coalescing free list
 struct Arena {
@@ -334,7 +360,8 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   }
   // depthwise layers the slab kernel covers (64-channel blocks, stride 1, wide maps) run on the tensor cores with
   // diagonal weight taps: the CUDA-core kernel is bound by its instruction count (~40 per output)
-  const bool dw_on_slab = !is_linear && groups == C && K == C && groups > 1 && in.cs == C && d.in1 < 0 && !getenv("TLXCV_NO_DW_SLAB") &&
+  if (out.cs != K && d.in1 >= 0) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: a residual add needs a multiple of 8 output channels");
+  const bool dw_on_slab = !is_linear && groups == C && K == C && groups > 1 && in.cs == C && d.in1 < 0 && !tuning_env("TLXCV_NO_DW_SLAB") &&
                           conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups);
   const bool depthwise = !is_linear && groups == C && K == C && groups > 1 && !dw_on_slab;
   if (depthwise) {
@@ -361,7 +388,7 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   op.weights = w;
   const __nv_bfloat16* act_in = reinterpret_cast<const __nv_bfloat16*>(p->arena + in.offset);
   int force_bn = 0;
-  if (const char* e = getenv("TLXCV_FORCE_BLOCK_N")) force_bn = atoi(e);
+  if (const char* e = tuning_env("TLXCV_FORCE_BLOCK_N")) force_bn = atoi(e);
   void* out_bf16 = nullptr;
   if (out.d.dtype != TLXCV_F32) {
     if (out.d.role != TLXCV_ROLE_INTERNAL) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: bf16 output must be an internal tensor");
@@ -376,7 +403,7 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   }
   if (d.act2 != TLXCV_ACT_NONE && d.act2 != TLXCV_ACT_RELU)
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: only ReLU (or nothing) may follow the residual add on the tensor-core path");
-  if (!is_linear && out_bf16 && in.cs == C && conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups)) {
+  if (!is_linear && out_bf16 && in.cs == C && out.cs == K && conv3x3_slab_supported(C, K, H, W, R, S, stride, pad, dil, groups)) {
     // 3x3 stride-1 layer with 64-channel work items: slab kernel (each input row fetched once, stationary weights)
     __nv_bfloat16* ws = w;
     int Kts = Ktot;
@@ -402,13 +429,12 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
       (d.act2 == TLXCV_ACT_LEAKY && !(d.alpha2 >= 0.0f && d.alpha2 <= 1.0f)))
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "conv: LeakyReLU slope outside [0, 1]");
   std::string err = tc_conv_prepare(op.tc, ctx->sm_count, act_in, N, H, W, C, in.cs, w, Ktot, K, R, S, stride, pad, dil,
-                                    groups, force_bn, out_bf16, res_bf16);
+                                    groups, force_bn, out_bf16, out.cs, res_bf16);
   if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
   ConvKernelParams& kp = op.tc.p;
   kp.scale = op.scale, kp.shift = op.shift;
   kp.act1 = d.act1, kp.alpha1 = d.alpha1, kp.act2 = d.act2, kp.alpha2 = d.alpha2;
   kp.out_f32 = out.d.dtype == TLXCV_F32;
-  if (kp.out_f32 && (K % 4)) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "fp32 conv output needs C_out %% 4 == 0");
   op.impl = kImplTcConv;
   char name[48];
   static const char* mnames[] = {"tiled", "im2col", "gatherc4"};
@@ -450,7 +476,7 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
       TLX_CUDA(ctx, conv3x3_slab_launch(op.slab, st));
       break;
     case kImplExport:
-      TLX_CUDA(ctx, export_nchw(pin, static_cast<float*>(pout), in.d.n, in.d.c, in.d.h, in.d.w, is_f32, st));
+      TLX_CUDA(ctx, export_nchw(pin, static_cast<float*>(pout), in.d.n, in.d.c, in.cs, in.d.h, in.d.w, is_f32, st));
       break;
     case kImplTcConv: {
       TcConvLaunch L = op.tc;
@@ -489,10 +515,10 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
   return TLXCV_OK;
 }
 
-int launch_all(tlxcv_plan* p, const void* const* inputs, void* const* outputs, cudaStream_t st) {
-  static const bool sync_each = getenv("TLXCV_SYNC_EACH_OP") != nullptr;  // debugging: attribute faults to an op
-  int i = 0;
-  for (OpRt& op : p->ops) {
+int launch_range(tlxcv_plan* p, int begin, int end, const void* const* inputs, void* const* outputs, cudaStream_t st) {
+  static const bool sync_each = tuning_env("TLXCV_SYNC_EACH_OP") != nullptr;  // debugging: attribute faults to an op
+  for (int i = begin; i < end; ++i) {
+    OpRt& op = p->ops[i];
     int rc = launch_op(p, op, inputs, outputs, st);
     if (rc != TLXCV_OK) return rc;
     if (sync_each) {
@@ -500,9 +526,43 @@ int launch_all(tlxcv_plan* p, const void* const* inputs, void* const* outputs, c
       if (e != cudaSuccess)
         return fail(p->ctx, TLXCV_ERR_CUDA, "op %d (%s) faulted: %s", i, op.info.kernel, cudaGetErrorString(e));
     }
-    ++i;
   }
   return TLXCV_OK;
+}
+
+int launch_all(tlxcv_plan* p, const void* const* inputs, void* const* outputs, cudaStream_t st) {
+  return launch_range(p, 0, static_cast<int>(p->ops.size()), inputs, outputs, st);
+}
+
+// Captures ops [begin, end) into an executable graph (on a private stream; the caller's stream is not touched).
+int capture_range(tlxcv_plan* p, int begin, int end, const void* const* inputs, void* const* outputs, cudaGraphExec_t* exec) {
+  tlxcv_ctx* ctx = p->ctx;
+  cudaStream_t cap;
+  TLX_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
+  int rc = TLXCV_OK;
+  if (e == cudaSuccess) {
+    rc = launch_range(p, begin, end, inputs, outputs, cap);
+    e = cudaStreamEndCapture(cap, &graph);
+  }
+  cudaStreamDestroy(cap);
+  if (rc != TLXCV_OK) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+  return TLXCV_OK;
+}
+
+bool touches_external(const tlxcv_plan* p, const OpRt& op) {
+  if (op.nop) return false;
+  for (int t : {op.d.in0, op.d.in1, op.d.out})
+    if (t >= 0 && p->tensors[t].d.role != TLXCV_ROLE_INTERNAL) return true;
+  return false;
 }
 
 }  // namespace
@@ -526,7 +586,7 @@ int tlxcv_create(int device, tlxcv_ctx** out) {
   if (prop.major != 10)
     return fail(nullptr, TLXCV_ERR_NO_DEVICE, "device %d is sm_%d%d; this library contains sm_100a (Blackwell B200) code only",
                 device, prop.major, prop.minor);
-  if (cudaSetDevice(device) != cudaSuccess) return fail(nullptr, TLXCV_ERR_CUDA, "cudaSetDevice failed");
+  DeviceGuard guard(device);
   cudaError_t e = tc_conv_set_attributes();
   if (e == cudaSuccess) e = stem_rowring_set_attributes();
   if (e == cudaSuccess) e = conv3x3_slab_set_attributes();
@@ -554,7 +614,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
   if (precision != TLXCV_PREC_BF16 && precision != TLXCV_PREC_F32_VALIDATE)
     return fail(ctx, TLXCV_ERR_INVALID, "plan_build: unknown precision %d", precision);
   *out = nullptr;
-  TLX_CUDA(ctx, cudaSetDevice(ctx->device));
+  DeviceGuard dev_guard(ctx->device);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   tlxcv_plan* p = new tlxcv_plan();
   p->ctx = ctx;
@@ -578,8 +638,9 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     if (T.d.dtype == TLXCV_ACT && T.d.role == TLXCV_ROLE_INTERNAL) {
       if (T.d.c <= 4)
         T.cs = 4;
-      else if (T.d.c % 8)
-        return fail(ctx, TLXCV_ERR_UNSUPPORTED, "tensor %d: activation channels (%d) must be <= 4 or a multiple of 8", i, T.d.c);
+      else if (T.d.c % 8 && !p->f32)
+        T.cs = static_cast<int>(align_up(T.d.c, 8));  // rows padded to 16 bytes: head convs (YOLOv3 outputs: 3 x (classes + 5)
+                                                      // channels); checked below: written by a conv, read by the export only
     }
     T.bytes = static_cast<size_t>(T.d.n) * T.d.h * T.d.w * T.cs * dtype_size(p, T.d.dtype);
     if (T.d.role == TLXCV_ROLE_INPUT) {
@@ -598,9 +659,23 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     if (d.in0 < 0 || d.in0 >= n_tensors || d.out < 0 || d.out >= n_tensors || d.in1 >= n_tensors)
       return fail(ctx, TLXCV_ERR_INVALID, "op %d: tensor index out of range", i);
   }
+  for (int i = 0; i < n_ops; ++i) {
+    const tlxcv_op_desc& d = ops[i];
+    for (int t : {d.in0, d.in1}) {
+      if (t < 0) continue;
+      const TensorRt& T = p->tensors[t];
+      if (T.d.role == TLXCV_ROLE_INTERNAL && T.d.dtype == TLXCV_ACT && T.d.c > 4 && T.d.c % 8 && d.kind != TLXCV_OP_EXPORT_NCHW)
+        return fail(ctx, TLXCV_ERR_UNSUPPORTED,
+                    "op %d reads tensor %d with %d channels: activations that feed another layer need a multiple of 8 channels "
+                    "(other widths are only supported for maps that are returned)", i, t, T.d.c);
+    }
+    const TensorRt& O = p->tensors[d.out];
+    if (O.d.role == TLXCV_ROLE_INTERNAL && O.d.dtype == TLXCV_ACT && O.d.c > 4 && O.d.c % 8 && d.kind != TLXCV_OP_CONV)
+      return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: only a convolution may produce a map with %d channels (not a multiple of 8)", i, O.d.c);
+  }
   // ---- pre-pass: C_in <= 4 stems go to the row-ring kernel (padded-column input written by the import
   //      op), and a 3x3/s2/p1 max-pool that is the stem's only consumer is fused into its epilogue ----
-  if (!p->f32 && !getenv("TLXCV_NO_ROWRING")) {
+  if (!p->f32 && !tuning_env("TLXCV_NO_ROWRING")) {
     for (int i = 0; i < n_ops; ++i) {
       OpRt& op = p->ops[i];
       const tlxcv_op_desc& d = op.d;
@@ -622,7 +697,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       op.geo = g;
       in.wp = g.Wp, in.pad_l = g.pad_l, in.cs = 4;
       in.bytes = static_cast<size_t>(in.d.n) * in.d.h * g.Wp * 4 * 2;
-      if (g.pairs || g.Qw > 128 || getenv("TLXCV_NO_POOL_FUSION")) continue;
+      if (g.pairs || g.Qw > 128 || tuning_env("TLXCV_NO_POOL_FUSION")) continue;
       int pool = -1, users = 0;
       for (int k = 0; k < n_ops; ++k)
         if (p->ops[k].d.in0 == d.out || p->ops[k].d.in1 == d.out) ++users, pool = k;
@@ -638,7 +713,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
   }
   // ---- pre-pass: `relu(bn(conv1x1(a)) + bn(conv1x1_stride(b)))` (last conv of a bottleneck + the block's
   //      downsample conv) becomes ONE dual-accumulator kernel: the residual map never reaches HBM ----
-  if (!p->f32 && !getenv("TLXCV_NO_DUAL")) {
+  if (!p->f32 && !tuning_env("TLXCV_NO_DUAL")) {
     for (int i = 0; i < n_ops; ++i) {
       OpRt& B = p->ops[i];
       const tlxcv_op_desc& d = B.d;
@@ -666,7 +741,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       if (x2.d.dtype != TLXCV_ACT || x2.d.c % 8 || x2.d.c <= 4) continue;
       // worth it only while the pair is bound by HBM traffic: the dual kernel works on 128-wide tiles, which costs
       // the MMA / L2-bound deep stages more than the saved residual round trip brings
-      if ((x2.d.c + 63) / 64 + (xin.d.c + 63) / 64 > 8 && !getenv("TLXCV_FORCE_DUAL")) continue;
+      if ((x2.d.c + 63) / 64 + (xin.d.c + 63) / 64 > 8 && !tuning_env("TLXCV_FORCE_DUAL")) continue;
       // a must not be rewritten between A and B (it is read later now): its producer precedes A by construction
       p->tensors[d.in1].elided = true;
       A.nop = true;
@@ -693,7 +768,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
   // ---- workspace: first-fit arena over tensor lifetimes ----
   {
     Arena arena;
-    const bool no_reuse = getenv("TLXCV_NO_REUSE") != nullptr;  // debugging: keep every intermediate readable
+    const bool no_reuse = tuning_env("TLXCV_NO_REUSE") != nullptr;  // debugging: keep every intermediate readable
     for (int i = 0; i < n_ops; ++i) {
       if (p->ops[i].nop) continue;
       TensorRt& o = p->tensors[p->ops[i].d.out];
@@ -743,7 +818,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         set_info(op, o.wp > 0 ? "import_u8_nhwc_padded" : "import_u8_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_EXPORT_NCHW:
-        if (o.d.role != TLXCV_ROLE_OUTPUT || o.d.dtype != TLXCV_F32 || in.d.dtype != TLXCV_ACT || in.cs != in.d.c)
+        if (o.d.role != TLXCV_ROLE_OUTPUT || o.d.dtype != TLXCV_F32 || in.d.dtype != TLXCV_ACT || in.wp > 0)
           return fail(ctx, TLXCV_ERR_INVALID, "op %d: export expects internal activation -> external f32", i);
         op.impl = kImplExport;
         set_info(op, "export_nchw_tile", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
@@ -787,6 +862,9 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       return fail(ctx, rc, "op %d: %s", i, msg.c_str());
     }
   }
+  // The packing / folding kernels above were enqueued on `st`; the plan may be run on ANY stream afterwards (a pipeline
+  // builds on one stream and runs on another), so the one-time preparation is complete before plan_build returns.
+  TLX_CUDA(ctx, cudaStreamSynchronize(st));
   guard.p = nullptr;
   *out = p;
   return TLXCV_OK;
@@ -794,9 +872,11 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
 
 int tlxcv_plan_destroy(tlxcv_plan* p) {
   if (!p) return TLXCV_OK;
-  cudaSetDevice(p->ctx->device);
+  DeviceGuard dev_guard(p->ctx->device);
   cudaDeviceSynchronize();
   for (auto& g : p->graphs) cudaGraphExecDestroy(g.second);
+  for (auto& sgm : p->segments)
+    if (sgm.exec) cudaGraphExecDestroy(sgm.exec);
   for (void* q : p->owned) cudaFree(q);
   for (void* q : p->stage_in) cudaFree(q);
   for (void* q : p->stage_out) cudaFree(q);
@@ -809,39 +889,55 @@ int tlxcv_plan_run(tlxcv_plan* p, const void* const* inputs, void* const* output
   if (!p || !inputs || !outputs) return TLXCV_ERR_INVALID;
   tlxcv_ctx* ctx = p->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(ctx->device);
   if (!use_graph) return launch_all(p, inputs, outputs, st);
+  std::lock_guard<std::mutex> lock(p->graphs_mu);
   std::vector<const void*> key;
   for (size_t i = 0; i < p->input_ids.size(); ++i) key.push_back(inputs[i]);
   for (size_t i = 0; i < p->output_ids.size(); ++i) key.push_back(outputs[i]);
-  cudaGraphExec_t exec = nullptr;
   for (auto& g : p->graphs)
-    if (g.first == key) exec = g.second;
-  if (!exec) {
+    if (g.first == key) {
+      TLX_CUDA(ctx, cudaGraphLaunch(g.second, st));
+      return TLXCV_OK;
+    }
+  bool seen = false;
+  for (auto& k : p->seen_keys) seen = seen || k == key;
+  if (seen) {  // the pointer set came back: worth a whole-forward graph
+    cudaGraphExec_t exec = nullptr;
+    int rc = capture_range(p, 0, static_cast<int>(p->ops.size()), inputs, outputs, &exec);
+    if (rc != TLXCV_OK) return rc;
     if (p->graphs.size() >= 8) {  // bounded cache: drop the oldest capture
       cudaGraphExecDestroy(p->graphs.front().second);
       p->graphs.erase(p->graphs.begin());
     }
-    cudaStream_t cap;
-    TLX_CUDA(ctx, cudaStreamCreateWithFlags(&cap, cudaStreamNonBlocking));
-    cudaGraph_t graph = nullptr;
-    cudaError_t e = cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal);
-    int rc = TLXCV_OK;
-    if (e == cudaSuccess) {
-      rc = launch_all(p, inputs, outputs, cap);
-      e = cudaStreamEndCapture(cap, &graph);
-    }
-    cudaStreamDestroy(cap);
-    if (rc != TLXCV_OK) {
-      if (graph) cudaGraphDestroy(graph);
-      return rc;
-    }
-    if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-    e = cudaGraphInstantiate(&exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e != cudaSuccess) return fail(ctx, TLXCV_ERR_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
     p->graphs.emplace_back(key, exec);
+    TLX_CUDA(ctx, cudaGraphLaunch(exec, st));
+    return TLXCV_OK;
   }
-  TLX_CUDA(ctx, cudaGraphLaunch(exec, st));
+  if (p->seen_keys.size() >= 16) p->seen_keys.erase(p->seen_keys.begin());
+  p->seen_keys.push_back(key);
+  if (p->segments.empty()) {
+    const int n = static_cast<int>(p->ops.size());
+    for (int i = 0; i < n;) {
+      const bool ext = touches_external(p, p->ops[i]);
+      int j = i + 1;
+      while (j < n && touches_external(p, p->ops[j]) == ext) ++j;
+      p->segments.push_back({i, j, !ext, nullptr});
+      i = j;
+    }
+  }
+  for (auto& sgm : p->segments) {
+    if (sgm.graphable && sgm.end - sgm.begin >= 2) {
+      if (!sgm.exec) {
+        int rc = capture_range(p, sgm.begin, sgm.end, inputs, outputs, &sgm.exec);
+        if (rc != TLXCV_OK) return rc;
+      }
+      TLX_CUDA(ctx, cudaGraphLaunch(sgm.exec, st));
+    } else {
+      int rc = launch_range(p, sgm.begin, sgm.end, inputs, outputs, st);
+      if (rc != TLXCV_OK) return rc;
+    }
+  }
   return TLXCV_OK;
 }
 
@@ -849,6 +945,7 @@ int tlxcv_plan_run_host(tlxcv_plan* p, const void* const* host_inputs, void* con
   if (!p || !host_inputs || !host_outputs) return TLXCV_ERR_INVALID;
   tlxcv_ctx* ctx = p->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(ctx->device);
   if (p->stage_in.empty() && p->stage_out.empty()) {
     for (int t : p->input_ids) {
       void* q = nullptr;
@@ -874,6 +971,7 @@ int tlxcv_plan_profile(tlxcv_plan* p, const void* const* inputs, void* const* ou
   if (!p || !per_op_ms || n_ops != static_cast<int>(p->ops.size())) return TLXCV_ERR_INVALID;
   tlxcv_ctx* ctx = p->ctx;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DeviceGuard dev_guard(ctx->device);
   std::vector<cudaEvent_t> ev(p->ops.size() + 1);
   for (auto& e : ev) TLX_CUDA(ctx, cudaEventCreate(&e));
   TLX_CUDA(ctx, cudaEventRecord(ev[0], st));

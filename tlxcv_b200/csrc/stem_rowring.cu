@@ -655,7 +655,7 @@ std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry
   p.pool = pool, p.Pp = Pp, p.Qp = Qp;
   p.out = static_cast<__nv_bfloat16*>(out);
   p.in = in_padded, p.Wp = g.Wp;
-  if (const char* e = getenv("TLXCV_DEBUG_ABLATE_STEM")) p.ablate = atoi(e);  // timing experiments only: results are wrong
+  if (const char* e = debug_env("TLXCV_DEBUG_ABLATE_STEM")) p.ablate = atoi(e);  // timing experiments only: results are wrong
   if (pool && (p.q_tiles != 1 || g.pairs)) return "stem: the fused max-pool needs a single column tile";
   // step / ring geometry
   p.G = kT * stride;
@@ -690,7 +690,7 @@ std::string stem_rowring_prepare(StemLaunch& L, int sm_count, const StemGeometry
     const long long cost = per_cta * (steps * 10 + 4);
     if (best < 0 || cost < best) best = cost, p.bands = bands, p.band_rows = rows;
   }
-  if (const char* e = getenv("TLXCV_DEBUG_STEM_BANDS")) {  // A/B timing only
+  if (const char* e = tuning_env("TLXCV_DEBUG_STEM_BANDS")) {  // A/B timing only
     const int bands = std::max(1, std::min(units, atoi(e)));
     p.band_rows = (units + bands - 1) / bands;
     p.bands = (units + p.band_rows - 1) / p.band_rows;

@@ -90,3 +90,70 @@ class ShardedForward:
         return self.forward_local(shard.contiguous(), n)
 
     __call__ = forward
+
+
+def pin_rank_affinity(local_rank: int, local_world: int) -> list[int]:
+    """Give each rank of a box its own contiguous slice of the host cores this process may use (the H2D staging and the
+    launch thread of eight ranks otherwise migrate over the same cores).  Returns the cores now allowed."""
+    try:
+        cores = sorted(os.sched_getaffinity(0))
+    except AttributeError:      # not Linux
+        return []
+    if local_world <= 1 or len(cores) < local_world:
+        return cores
+    per = len(cores) // local_world
+    mine = cores[local_rank * per:(local_rank + 1) * per]
+    os.sched_setaffinity(0, mine)
+    return mine
+
+
+class OverlappedGather:
+    """Forward of step i on the compute stream while the logits of step i-1 are all-gathered on a side stream.
+
+    The all-gather of one step's logits (1 MB per rank) is pure latency (~0.1 ms over NVLink at 8 GPUs); issued on the
+    compute stream after every forward it costs 3 % of the step.  Here every step writes its logits into one of ``depth``
+    slots, records an event, and the collective of that slot runs on ``gather_stream`` behind the event while the compute
+    stream is already in the next forward.  ``step`` only waits (on the device) for the gather that last used the slot
+    it is about to overwrite."""
+
+    def __init__(self, plan, world: int, device, depth: int = 2, group=None):
+        import torch.cuda as cuda
+
+        self.plan, self.world, self.group, self.depth = plan, world, group, depth
+        self.local = [plan.alloc_outputs() for _ in range(depth)]
+        rows = self.local[0][0].shape[0]
+        self.gathered = [torch.empty((world * rows,) + tuple(self.local[0][0].shape[1:]), dtype=self.local[0][0].dtype,
+                                     device=device) for _ in range(depth)] if world > 1 else None
+        self.gather_stream = cuda.Stream(device) if world > 1 else None
+        self.ev_fwd = [cuda.Event() for _ in range(depth)]
+        self.ev_gathered = [cuda.Event() for _ in range(depth)]
+        self._i = 0
+
+    def step(self, inputs):
+        """Enqueue one forward (+ the gather of its logits); returns the slot index."""
+        slot = self._i % self.depth
+        self._i += 1
+        cur = torch.cuda.current_stream()
+        if self.world > 1:
+            cur.wait_event(self.ev_gathered[slot])        # the gather that read this slot's logits last time has finished
+        self.plan.run(inputs, self.local[slot], graph=True)
+        if self.world > 1:
+            self.ev_fwd[slot].record(cur)
+            with torch.cuda.stream(self.gather_stream):
+                self.gather_stream.wait_event(self.ev_fwd[slot])
+                dist.all_gather_into_tensor(self.gathered[slot], self.local[slot][0], group=self.group)
+                self.ev_gathered[slot].record(self.gather_stream)
+        return slot
+
+    def result(self, slot):
+        """Gathered rows of ``slot`` (device tensor); the caller's stream waits for the collective."""
+        if self.world == 1:
+            return self.local[slot][0]
+        torch.cuda.current_stream().wait_event(self.ev_gathered[slot])
+        return self.gathered[slot]
+
+    def drain(self):
+        """Make the current stream wait for every outstanding gather (end of a timed region)."""
+        if self.world > 1:
+            for ev in self.ev_gathered:
+                torch.cuda.current_stream().wait_event(ev)

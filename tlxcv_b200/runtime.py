@@ -262,7 +262,7 @@ class Plan:
         """Debug: copy internal tensor ``index`` out as (N, H, W, C_storage) in the plan's activation dtype."""
         t = self.spec.tensors[index]
         dt = torch.float32 if self.precision == PREC_F32 else torch.bfloat16
-        cs = 4 if t.c <= 4 else t.c
+        cs = 4 if t.c <= 4 else (t.c if self.precision == PREC_F32 else (t.c + 7) // 8 * 8)
         buf = torch.empty((t.n, t.h, t.w, cs), dtype=dt, device=self.device)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.ctx.lib.tlxcv_plan_read_tensor(self.handle, index, C.c_void_p(buf.data_ptr()),
