@@ -19,6 +19,8 @@
  *   nn.MaxPool2d                                                    TLXCV_OP_MAXPOOL
  *   nn.AdaptiveAvgPool2d(1)                                         TLXCV_OP_GAP
  *   nn.Linear                                                       TLXCV_OP_LINEAR
+ *   Interpolater (nearest x2) + tlx.concat  detection/yolov3.py:244,252  TLXCV_OP_UPSAMPLE_CONCAT
+ *   YOLOv3FPN / YOLOv3Head convs     detection/yolov3.py:122-258,306-378  TLXCV_OP_CONV (bias, any C_out)
  *   Module construction / set_eval (weights become static)          tlxcv_plan_build
  *
  * Conventions
@@ -72,10 +74,13 @@ typedef enum {
   TLXCV_OP_ADD_ACT = 5,      /* act2(in0 [+ in1]) — only for adds / activations no conv could absorb */
   TLXCV_OP_ARGMAX = 6,       /* (N, K) fp32 -> (N) int64                                           */
   TLXCV_OP_EXPORT_NCHW = 7,  /* internal NHWC activation -> external NCHW fp32                     */
-  TLXCV_OP_IMPORT_U8_NHWC = 8 /* external NHWC uint8 image batch (N, H, W, C<=4) -> internal activation
+  TLXCV_OP_IMPORT_U8_NHWC = 8, /* external NHWC uint8 image batch (N, H, W, C<=4) -> internal activation
                                  (x - mean[c]) / std[c]: the reference's host-side Normalize + ToTensor
                                  (demo/image_classification/predict-resnet.py:50-54) fused into the layout
                                  pass; bn_mean / bn_var carry device pointers to float mean[C] / std[C]      */
+  TLXCV_OP_UPSAMPLE_CONCAT = 9 /* out[..., :C0] = in0 nearest-up-sampled r times, out[..., C0:] = in1 up-sampled s
+                                 times (in1 = -1: up-sampling alone; r = s = 1: channel concat): Interpolater +
+                                 tlx.concat of YOLOv3FPN.forward (detection/yolov3.py:244,252-253) in one pass          */
 } tlxcv_op_kind;
 
 typedef enum { TLXCV_ACT_NONE = 0, TLXCV_ACT_RELU = 1, TLXCV_ACT_RELU6 = 2, TLXCV_ACT_LEAKY = 3 } tlxcv_act;

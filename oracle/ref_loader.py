@@ -61,6 +61,68 @@ def load_reference_module(key: str, shim=None):
     return mod
 
 
+_PKG = "_tlxcv_ref"
+
+
+def load_reference_package_module(dotted: str, shim=None):
+    """Import ``tlxcv.<dotted>`` (e.g. ``models.detection.yolov3``) from the reference tree WITH its relative imports
+    (``from .backbones.darknet import ...``, ``from .utils.layers import Interpolater``) but without executing
+    ``tlxcv/__init__.py`` / ``tlxcv/models/__init__.py`` (which star-import every family): the parent packages are
+    empty namespace stand-ins whose ``__path__`` points into the reference tree."""
+    import types
+
+    parts = dotted.split(".")
+    shim = shim or tlx_compat.installed
+    created = []
+    with shim():
+        try:
+            for i in range(len(parts)):
+                name = ".".join([_PKG] + parts[:i])
+                path = os.path.join(REFERENCE_ROOT, "tlxcv", *parts[:i])
+                if not os.path.isdir(path):
+                    raise FileNotFoundError(path)
+                if name not in sys.modules:
+                    m = types.ModuleType(name)
+                    m.__path__, m.__package__ = [path], name
+                    sys.modules[name] = m
+                    created.append(name)
+            return importlib.import_module(".".join([_PKG] + parts))
+        finally:
+            # the stand-in packages and everything imported under them go away again (the next shim must re-import)
+            for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + ".")]:
+                del sys.modules[k]
+
+
+def _build_yolov3(shim=None, **kw):
+    """DarkNet-53 -> YOLOv3FPN -> YOLOv3Head of the reference (detection/yolov3.py:51-68 without the host-side
+    post-processing): returns the raw head maps the way ``YOLOv3.forward`` computes them in eval mode."""
+    y = load_reference_package_module("models.detection.yolov3", shim)
+    shim = shim or tlx_compat.installed
+    with shim():
+        nn = sys.modules["tensorlayerx.nn"]
+
+        class YOLOv3Net(nn.Module):
+            def __init__(self):
+                super().__init__()
+                self.backbone = y.DarkNet()
+                self.neck = y.YOLOv3FPN()
+                self.yolo_head = y.YOLOv3Head(**kw)
+
+            def forward(self, inputs):
+                body_feats = self.backbone(inputs)
+                neck_feats = self.neck(body_feats, False)
+                return {"body_feats": body_feats, "neck_feats": neck_feats, "yolo_head_outs": self.yolo_head(neck_feats)}
+
+        return YOLOv3Net()
+
+
+def _build_det_mobilenet(shim=None, **kw):
+    m = load_reference_package_module("models.detection.backbones.mobilenet_v1", shim)
+    shim = shim or tlx_compat.installed
+    with shim():
+        return m.MobileNet(**kw)
+
+
 # constructor table: name -> (file key, callable name, kwargs)
 MODELS = {
     "resnet18": ("resnet", "resnet18", {}),
@@ -77,8 +139,13 @@ MODELS = {
 }
 
 
+PACKAGE_MODELS = {"yolov3_darknet53": _build_yolov3, "mobilenet_v1_det": _build_det_mobilenet}
+
+
 def build(name: str, shim=None, **kwargs):
-    """Construct reference model ``name`` (see MODELS) from its own file."""
+    """Construct reference model ``name`` (see MODELS / PACKAGE_MODELS) from its own file."""
+    if name in PACKAGE_MODELS:
+        return PACKAGE_MODELS[name](shim, **kwargs)
     key, fn, kw = MODELS[name]
     mod = load_reference_module(key, shim)
     kw = dict(kw, **kwargs)

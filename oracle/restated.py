@@ -265,6 +265,64 @@ def darknet53_det(sd, inputs, return_idx=(2, 3, 4), taps=None):
     return blocks
 
 
+def yolov3_darknet53(sd, inputs, taps=None):
+    """DarkNet-53 -> YOLOv3FPN -> YOLOv3Head output convs (detection/yolov3.py:51-68 without post-processing).
+
+    YoloDetBlock :178-180 (conv_module = 1x1, 3x3, 1x1, 3x3, 1x1 ConvBN+LeakyReLU; tip = 3x3), YOLOv3FPN.forward
+    :233-258 (deepest map first; route -> 1x1 ConvBN -> nearest x2 -> concat([route, x], axis=1)), YOLOv3Head.forward
+    :353 (1x1 conv with bias per level)."""
+    p = _P(sd, "", taps)
+    body = darknet53_det(_SubDict(sd, "backbone."), inputs)
+    neck, route = [], None
+    for i, x in enumerate(body[::-1]):
+        if i > 0:
+            x = torch.cat([route, x], dim=1)                            # :244
+        bp = p.sub(f"neck.yolo_blocks.{i}")
+        for j, k in enumerate([1, 3, 1, 3, 1]):                         # :146-152
+            x = _dk_det_cbl(bp.sub(f"conv_module.{j}"), x, 1, (k - 1) // 2)
+        route = x
+        neck.append(_dk_det_cbl(bp.sub("tip"), route, 1, 1))            # :179
+        if i < 2:
+            route = _dk_det_cbl(p.sub(f"neck.routes.{i}"), route, 1, 0)     # :251
+            route = F.interpolate(route, scale_factor=2.0)              # :252-253 (nearest)
+    heads = [conv(p.sub(f"yolo_head.yolo_outputs.{i}"), f) for i, f in enumerate(neck)]    # :353
+    return {"body_feats": body, "neck_feats": neck, "yolo_head_outs": heads}
+
+
+class _SubDict:
+    """Read-only view of a state dict under a key prefix."""
+
+    def __init__(self, sd, prefix):
+        self.sd, self.prefix = sd, prefix
+
+    def __getitem__(self, k):
+        return self.sd[self.prefix + k]
+
+    def get(self, k, default=None):
+        return self.sd.get(self.prefix + k, default)
+
+
+def mobilenet_v1_det(sd, inputs, feature_maps=(4, 6, 13), taps=None):
+    """detection/backbones/mobilenet_v1.py:238-245 (ConvBNLayer :44-50: conv, BN, ReLU; DepthwiseSeparable :99-103)."""
+    p = _P(sd, "", taps)
+    x = inputs["images"] if isinstance(inputs, dict) else inputs
+
+    def cbl(q, x, k, stride, groups=1):
+        return F.relu(bn(q.sub("my_batch_norm"), conv(q.sub("_conv"), x, stride, (k - 1) // 2, groups)))
+
+    cfg = [(32, 64, 1), (64, 128, 2), (128, 128, 1), (128, 256, 2), (256, 256, 1), (256, 512, 2)] + \
+          [(512, 512, 1)] * 5 + [(512, 1024, 2), (1024, 1024, 1)]        # :199-209
+    y = cbl(p.sub("conv1"), x, 3, 2)
+    outs = []
+    for idx, (c1, c2, s) in enumerate(cfg, start=1):
+        bp = p.sub(f"dwsl.{idx - 1}")
+        y = cbl(bp.sub("_depthwise_conv"), y, 3, s, c1)
+        y = cbl(bp.sub("_pointwise_conv"), y, 1, 1)
+        if idx in feature_maps:
+            outs.append(y)
+    return outs
+
+
 FORWARD = {
     "resnet18": lambda sd, x, **k: resnet(sd, x, 18, **k),
     "resnet34": lambda sd, x, **k: resnet(sd, x, 34, **k),
@@ -277,6 +335,8 @@ FORWARD = {
     "mobilenet_v2": mobilenet_v2,
     "darknet53_cls": darknet53_cls,
     "darknet53_det": darknet53_det,
+    "yolov3_darknet53": yolov3_darknet53,
+    "mobilenet_v1_det": mobilenet_v1_det,
 }
 
 

@@ -276,6 +276,10 @@ def get_tensor_shape(x):
     return list(x.shape)
 
 
+def concat(values, axis=0):
+    return torch.cat(list(values), dim=axis)
+
+
 class _Init:
     """Inert initializer: weights are injected by the harness."""
 
@@ -305,7 +309,7 @@ def _build_modules():
     nn.Conv2d = GroupConv2d
     nn.Layer = Module
     nn.initializers = init
-    for fn in (add, relu, reshape, flatten, squeeze, argmax, get_tensor_shape):
+    for fn in (add, relu, reshape, flatten, squeeze, argmax, get_tensor_shape, concat):
         setattr(tlx, fn.__name__, fn)
         setattr(ops, fn.__name__, fn)
     tlx.FlattenReshape = FlattenReshape

@@ -27,7 +27,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)
 sys.path.insert(0, ROOT)
 
 from oracle import ref_loader  # noqa: E402
-from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, structured_images, synthetic_images  # noqa: E402
+from tlxcv_b200.testing import (flatten_outputs, model_input, seeded_state_dict, state_dict_digest,  # noqa: E402
+                                structured_images, synthetic_images)
 
 # model -> (n_images, image size)
 CASES = {
@@ -38,6 +39,8 @@ CASES = {
     "mobilenet_v2": (2, 224),
     "darknet53_cls": (2, 224),
     "darknet53_det": (1, 64),
+    "yolov3_darknet53": (1, 64),          # backbone + YOLOv3FPN + head output convs: 9 maps
+    "mobilenet_v1_det": (2, 96),
 }
 MANIFEST_ONLY = ["resnet34", "resnet101", "wide_resnet50_2", "resnext50_64x4d"]
 
@@ -51,6 +54,7 @@ FULL_SIZE = {
     "mobilenet_v2_bs64": ("mobilenet_v2", 64, 224, False),
     "resnext50_32x4d_bs64": ("resnext50_32x4d", 64, 224, False),
     "darknet53_det_608": ("darknet53_det", 2, 608, True),
+    "yolov3_darknet53_608": ("yolov3_darknet53", 1, 608, True),
 }
 SUB = (slice(None), slice(None, None, 4), slice(None, None, 3), slice(None, None, 3))
 
@@ -71,8 +75,7 @@ def main():
         model.set_eval()
         x = synthetic_images(n, size)
         with torch.no_grad():
-            y = model({"images": x}) if name == "darknet53_det" else model(x)
-        outs = y if isinstance(y, (list, tuple)) else [y]
+            outs = flatten_outputs(model(model_input(name, x)))
         arrays = {f"out{i}": o.numpy() for i, o in enumerate(outs)}
         np.savez_compressed(
             os.path.join(out_dir, f"{name}.npz"),
@@ -89,8 +92,7 @@ def main():
         model.set_eval()
         x = structured_images(n, size)
         with torch.no_grad():
-            y = model({"images": x}) if name == "darknet53_det" else model(x)
-        outs = y if isinstance(y, (list, tuple)) else [y]
+            outs = flatten_outputs(model(model_input(name, x)))
         arrays = {}
         for i, o in enumerate(outs):
             arrays[f"out{i}"] = (o[SUB] if sub else o).contiguous().numpy()

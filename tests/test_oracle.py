@@ -12,9 +12,12 @@ import pytest
 import torch
 
 from oracle import ref_loader, restated, tlx_compat
-from tlxcv_b200.testing import seeded_state_dict, state_dict_digest, structured_images, synthetic_images
+from tlxcv_b200.testing import (flatten_outputs, model_input, seeded_state_dict, state_dict_digest, structured_images,
+                                synthetic_images)
 
-GOLDEN = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls", "darknet53_det"]
+GOLDEN = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls", "darknet53_det",
+          "yolov3_darknet53", "mobilenet_v1_det"]
+CLASSIFIERS = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls"]
 # fixtures were minted with oneDNN on the build container's CPU; another CPU may pick other conv kernels
 ATOL = 2e-5
 
@@ -32,17 +35,16 @@ def test_restated_matches_golden(name, golden_dir, manifests):
     assert state_dict_digest(sd) == wdig, "seeded weight recipe drifted from the one the fixtures were minted with"
     x = synthetic_images(n, size)
     assert state_dict_digest({"x": x}) == idig
-    y = restated.forward(name, sd, {"images": x} if name == "darknet53_det" else x)
-    ys = y if isinstance(y, list) else [y]
+    ys = flatten_outputs(restated.forward(name, sd, model_input(name, x)))
     assert len(ys) == len(outs)
     for a, b in zip(ys, outs):
         assert a.shape == b.shape
         assert float((a - b).abs().max()) <= ATOL * max(1.0, float(b.abs().max()))
-    if name != "darknet53_det":
+    if name in CLASSIFIERS:
         assert torch.equal(ys[0].argmax(1), outs[0].argmax(1))
 
 
-FULL_SIZE = ["resnet50_bs256", "mobilenet_v2_bs64", "resnext50_32x4d_bs64", "darknet53_det_608"]
+FULL_SIZE = ["resnet50_bs256", "mobilenet_v2_bs64", "resnext50_32x4d_bs64", "darknet53_det_608", "yolov3_darknet53_608"]
 SUB = (slice(None), slice(None, None, 4), slice(None, None, 3), slice(None, None, 3))
 
 
@@ -56,8 +58,7 @@ def test_restated_matches_full_size_golden(fname, golden_dir, manifests):
     assert state_dict_digest(sd) == str(g["weight_digest"])
     x = structured_images(n, size)
     assert state_dict_digest({"x": x}) == str(g["input_digest"])
-    y = restated.forward(name, sd, {"images": x} if name == "darknet53_det" else x)
-    ys = y if isinstance(y, list) else [y]
+    ys = flatten_outputs(restated.forward(name, sd, model_input(name, x)))
     for i, a in enumerate(ys):
         b = torch.from_numpy(g[f"out{i}"])
         scale = max(1.0, float(b.abs().max()))
@@ -74,7 +75,7 @@ def test_restated_matches_full_size_golden(fname, golden_dir, manifests):
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")
 @pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d", "mobilenet_v2", "mobilenet_v1", "darknet53_cls",
-                                  "darknet53_det"])
+                                  "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det"])
 def test_restated_matches_reference_files_live(name):
     """Bit-for-bit: the restatement and the reference's own file, same weights, same input."""
     torch.manual_seed(0)
@@ -82,17 +83,18 @@ def test_restated_matches_reference_files_live(name):
     sd = seeded_state_dict(model.state_dict(), name, seed=77)
     model.load_state_dict(sd)
     model.set_eval()
-    x = synthetic_images(1, 64 if name == "darknet53_det" else 96, seed=5)
+    x = synthetic_images(1, 64 if name in ("darknet53_det", "yolov3_darknet53") else 96, seed=5)
     with torch.no_grad():
-        ref = model({"images": x}) if name == "darknet53_det" else model(x)
-    got = restated.forward(name, sd, {"images": x} if name == "darknet53_det" else x)
-    for a, b in zip(got if isinstance(got, list) else [got], ref if isinstance(ref, list) else [ref]):
+        ref = flatten_outputs(model(model_input(name, x)))
+    got = flatten_outputs(restated.forward(name, sd, model_input(name, x)))
+    assert len(got) == len(ref)
+    for a, b in zip(got, ref):
         assert torch.equal(a, b)
 
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")
 def test_reference_manifests_match_committed(manifests):
-    for name in ("resnet50", "mobilenet_v2", "darknet53_det"):
+    for name in ("resnet50", "mobilenet_v2", "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det"):
         model = ref_loader.build(name)
         assert [(k, tuple(v.shape)) for k, v in model.state_dict().items()] == manifests[name]
 

@@ -91,7 +91,7 @@ def test_predict_is_one_plan_with_argmax():
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")
 @pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls",
-                                  "darknet53_det"])
+                                  "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det"])
 def test_reference_files_run_unmodified_on_the_product_shim(name, manifests):
     """Drop-in: the reference's own model file, imported against tlxcv_b200 installed as `tensorlayerx`,
     builds B200-backed modules with the reference manifest and traces to the same plan as our model."""
@@ -112,7 +112,8 @@ def test_reference_files_run_unmodified_on_the_product_shim(name, manifests):
     assert [(k, tuple(v.shape)) for k, v in ref_model.state_dict().items()] == manifests[name]
     ref_model.set_eval()
     ours = models.REGISTRY[name]().set_eval()
-    arg = {"images": Shape(1, 3, 96, 96)} if name == "darknet53_det" else Shape(1, 3, 96, 96)
+    from tlxcv_b200.testing import DICT_INPUT
+    arg = {"images": Shape(1, 3, 96, 96)} if name in DICT_INPUT else Shape(1, 3, 96, 96)
     a, _ = planner.plan_for_shapes(ref_model, arg)
     b, _ = planner.plan_for_shapes(ours, arg)
     key = lambda s: [(o.kind, o.in0, o.in1, o.out, o.r, o.s, o.stride, o.pad, o.groups, o.act1, o.act2, o.path)  # noqa: E731

@@ -80,6 +80,12 @@ def argmax(x, axis=None):
     return _traced(x, "argmax").argmax(x, -1 if axis is None else axis)
 
 
+def concat(values, axis=0):
+    """``tlx.concat([route, x], axis=1)`` (detection/yolov3.py:244)."""
+    values = list(values)
+    return _traced(values[0], "concat").concat(values, axis)
+
+
 def get_tensor_shape(x):
     return list(x.shape)
 
@@ -102,6 +108,7 @@ class _Ops:
     reshape = staticmethod(reshape)
     flatten = staticmethod(flatten)
     argmax = staticmethod(argmax)
+    concat = staticmethod(concat)
 
 
 ops = _Ops()
@@ -120,7 +127,7 @@ def _shim_modules():
 
     me = sys.modules[__name__]
     ops_mod = types.ModuleType("tensorlayerx.ops")
-    for k in ("squeeze", "add", "relu", "reshape", "flatten", "argmax"):
+    for k in ("squeeze", "add", "relu", "reshape", "flatten", "argmax", "concat"):
         setattr(ops_mod, k, getattr(_Ops, k))
     return {"tensorlayerx": me, "tensorlayerx.nn": nn, "tensorlayerx.nn.initializers": nn.initializers,
             "tensorlayerx.ops": ops_mod, "tensorlayerx.initializers": nn.initializers}

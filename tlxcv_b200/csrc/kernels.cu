@@ -531,6 +531,33 @@ __global__ void add_act_kernel(const T* __restrict__ a, const T* __restrict__ b,
   Vec8<T>::store(dst + idx * 8, x);
 }
 
+// out[n][y][x][0:C0] = a[n][y / ra][x / ra][:],  out[n][y][x][C0:C0+C1] = b[n][y / rb][x / rb][:]   (nearest up-sampling by
+// integer factors + channel concat in ONE pass: Interpolater + tlx.concat of YOLOv3FPN.forward, detection/yolov3.py:244-253).
+// One thread per 8 output channels (16 B for bf16); b == nullptr: up-sampling alone.
+template <typename T>
+__global__ void upsample_concat_kernel(const T* __restrict__ a, const T* __restrict__ b, T* __restrict__ dst, int H, int W,
+                                       int C0_8, int C1_8, int ra, int rb, size_t total) {
+  pdl_wait();
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int C8 = C0_8 + C1_8;
+  const int c8 = static_cast<int>(idx % C8);
+  size_t pix = idx / C8;
+  const int x = static_cast<int>(pix % W);
+  pix /= W;
+  const int y = static_cast<int>(pix % H);
+  const size_t n = pix / H;
+  float v[8];
+  if (c8 < C0_8) {
+    const int Ha = H / ra, Wa = W / ra;
+    Vec8<T>::load(a + ((n * Ha + y / ra) * Wa + x / ra) * (static_cast<size_t>(C0_8) * 8) + c8 * 8, v);
+  } else {
+    const int Hb = H / rb, Wb = W / rb;
+    Vec8<T>::load(b + ((n * Hb + y / rb) * Wb + x / rb) * (static_cast<size_t>(C1_8) * 8) + (c8 - C0_8) * 8, v);
+  }
+  Vec8<T>::store(dst + idx * 8, v);
+}
+
 // one warp per row; first maximal index wins (torch.argmax on ties returns the first occurrence)
 __global__ void argmax_rows_kernel(const float* __restrict__ logits, long long* __restrict__ dst, int N, int K) {
   pdl_wait();
@@ -866,6 +893,17 @@ cudaError_t add_act(const void* a, const void* b, void* dst, size_t n, int act, 
     TLXCV_LAUNCH(add_act_kernel<float>, blocks_for(n8), kThreads, 0, st, static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(dst), n8, act, alpha);
   else
     TLXCV_LAUNCH(add_act_kernel<__nv_bfloat16>, blocks_for(n8), kThreads, 0, st, static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(dst), n8, act, alpha);
+  return cudaGetLastError();
+}
+
+cudaError_t upsample_concat(const void* a, const void* b, void* dst, int N, int H, int W, int C0, int C1, int ra, int rb,
+                            int is_f32, cudaStream_t st) {
+  if (C0 % 8 || C1 % 8 || ra < 1 || rb < 1 || H % ra || W % ra || H % rb || W % rb || (b == nullptr && C1 != 0)) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * H * W * ((C0 + C1) / 8);
+  if (is_f32)
+    TLXCV_LAUNCH(upsample_concat_kernel<float>, blocks_for(total), kThreads, 0, st, static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(dst), H, W, C0 / 8, C1 / 8, ra, rb, total);
+  else
+    TLXCV_LAUNCH(upsample_concat_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b), static_cast<__nv_bfloat16*>(dst), H, W, C0 / 8, C1 / 8, ra, rb, total);
   return cudaGetLastError();
 }
 

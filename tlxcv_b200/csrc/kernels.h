@@ -193,6 +193,9 @@ cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const flo
                         int act1, float alpha1, int act2, float alpha2, int is_f32, cudaStream_t st);
 cudaError_t add_act(const void* a, const void* b, void* dst, size_t n, int act, float alpha, int is_f32, cudaStream_t st);
 cudaError_t argmax_rows(const float* logits, long long* dst, int N, int K, cudaStream_t st);
+// dst[N][H][W][C0 + C1]: channels [0, C0) = a nearest-up-sampled ra times, [C0, C0 + C1) = b up-sampled rb times (b may be NULL)
+cudaError_t upsample_concat(const void* a, const void* b, void* dst, int N, int H, int W, int C0, int C1, int ra, int rb,
+                            int is_f32, cudaStream_t st);
 // fp32 direct conv on CUDA cores (validation mode; dense, grouped and depthwise)
 cudaError_t conv_direct_f32(const float* in, const float* w_rsck, float* out, const float* scale, const float* shift,
                             const float* residual, int N, int H, int W, int C, int P, int Q, int K, int R, int S,

@@ -31,7 +31,7 @@ struct TensorRt {
 };
 
 enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
-                  kImplStem, kImplSlab, kImplNop, kImplImportU8 };
+                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat };
 
 struct OpRt {
   tlxcv_op_desc d;
@@ -506,6 +506,10 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
     case kImplAddAct:
       TLX_CUDA(ctx, add_act(pin, pres, pout, static_cast<size_t>(in.d.n) * in.d.h * in.d.w * in.d.c, d.act2, d.alpha2, is_f32, st));
       break;
+    case kImplUpsampleConcat:
+      TLX_CUDA(ctx, upsample_concat(pin, pres, pout, out.d.n, out.d.h, out.d.w, in.d.c, d.in1 >= 0 ? p->tensors[d.in1].d.c : 0, d.r,
+                                    d.s, is_f32, st));
+      break;
     case kImplArgmax:
       TLX_CUDA(ctx, argmax_rows(static_cast<const float*>(pin), static_cast<long long*>(pout), in.d.n, in.d.c, st));
       break;
@@ -849,6 +853,21 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         op.impl = kImplAddAct;
         set_info(op, "add_act", 1, 0, 0, in_bytes * (d.in1 >= 0 ? 2 : 1) + out_bytes, 0, 256, 0, 0);
         break;
+      case TLXCV_OP_UPSAMPLE_CONCAT: {
+        const TensorRt* b = d.in1 >= 0 ? &p->tensors[d.in1] : nullptr;
+        const int c1 = b ? b->d.c : 0;
+        if (d.r < 1 || d.s < 1 || in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_ACT || o.d.role != TLXCV_ROLE_INTERNAL ||
+            in.d.role != TLXCV_ROLE_INTERNAL || (b && (b->d.dtype != TLXCV_ACT || b->d.role != TLXCV_ROLE_INTERNAL)))
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: upsample_concat works on internal activation tensors", i);
+        if (in.d.c % 8 || c1 % 8 || in.cs != in.d.c || (b && b->cs != b->d.c))
+          return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: upsample_concat needs channel counts that are multiples of 8", i);
+        if (o.d.n != in.d.n || o.d.c != in.d.c + c1 || o.d.h != in.d.h * d.r || o.d.w != in.d.w * d.r ||
+            (b && (b->d.n != in.d.n || o.d.h != b->d.h * d.s || o.d.w != b->d.w * d.s)))
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: upsample_concat output shape mismatch", i);
+        op.impl = kImplUpsampleConcat;
+        set_info(op, "upsample_concat", 1, 0, 0, in_bytes + (b ? static_cast<double>(b->bytes) : 0.0) + out_bytes, 0, 256, 0, 0);
+        break;
+      }
       case TLXCV_OP_ARGMAX:
         if (in.d.dtype != TLXCV_F32 || o.d.dtype != TLXCV_I64) return fail(ctx, TLXCV_ERR_INVALID, "op %d: argmax expects f32 -> i64", i);
         op.impl = kImplArgmax;

@@ -27,7 +27,7 @@ def active() -> "Graph | None":
 
 @dataclass
 class Node:
-    op: str                       # conv | bn | act | add | maxpool | gap | reshape | linear | argmax
+    op: str                       # conv | bn | act | add | maxpool | gap | reshape | linear | argmax | upsample | concat | ...
     inputs: list[int]
     out: int
     attrs: dict[str, Any] = field(default_factory=dict)
@@ -67,6 +67,26 @@ class SymTensor:
 
     def __repr__(self):
         return f"SymTensor(id={self.id}, shape={self.shape}, dtype={self.dtype})"
+
+    # The reference's torch-backend helpers call torch functions on the activation itself
+    # (detection/utils/ops.py:474-476: `F.interpolate(x, scale_factor=2.0)` behind `Interpolater`): route the few that
+    # are on the hot path into the trace, refuse the rest loudly.
+    @classmethod
+    def __torch_function__(cls, func, types, args=(), kwargs=None):
+        kwargs = kwargs or {}
+        name = getattr(func, "__name__", str(func))
+        if name == "interpolate":
+            x = args[0] if args else kwargs["input"]
+            return x.graph.interpolate(x, size=kwargs.get("size", args[1] if len(args) > 1 else None),
+                                       scale_factor=kwargs.get("scale_factor", args[2] if len(args) > 2 else None),
+                                       mode=kwargs.get("mode", args[3] if len(args) > 3 else "nearest"))
+        if name in ("cat", "concat", "concatenate"):
+            xs = args[0] if args else kwargs["tensors"]
+            dim = kwargs.get("dim", kwargs.get("axis", args[1] if len(args) > 1 else 0))
+            return xs[0].graph.concat(list(xs), dim)
+        if name == "relu":
+            return args[0].graph.act(args[0], "relu")
+        raise NotImplementedError(f"torch.{name} on a traced activation is not on the B200 hot path")
 
 
 class Graph:
@@ -135,6 +155,34 @@ class Graph:
         if a.shape != b.shape:
             raise ValueError(f"add: shape mismatch {a.shape} vs {b.shape}")
         return self._emit("add", [a, b], a.shape)
+
+    def interpolate(self, x, size=None, scale_factor=None, mode="nearest") -> SymTensor:
+        """Nearest-neighbour up-sampling by an integer factor (YOLOv3FPN route, detection/yolov3.py:252-253)."""
+        n, c, h, w = _nchw(x, "interpolate")
+        if mode != "nearest":
+            raise NotImplementedError(f"interpolate(mode={mode!r}): only nearest is on the hot path")
+        if size is not None:
+            sh, sw = (size, size) if isinstance(size, int) else tuple(size)
+            if sh % h or sw % w or sh // h != sw // w:
+                raise NotImplementedError(f"interpolate to {size} from {(h, w)}: only integer up-scaling")
+            k = sh // h
+        else:
+            if scale_factor is None or float(scale_factor) != int(scale_factor) or int(scale_factor) < 1:
+                raise NotImplementedError(f"interpolate(scale_factor={scale_factor}): only integer up-scaling")
+            k = int(scale_factor)
+        return self._emit("upsample", [x], (n, c, h * k, w * k), dict(scale=k))
+
+    def concat(self, xs, axis=1) -> SymTensor:
+        """Channel concatenation of (N, C_i, H, W) maps (``tlx.concat([route, x], axis=1)``, detection/yolov3.py:244)."""
+        if len(xs) < 2:
+            raise ValueError("concat needs at least two tensors")
+        shapes = [_nchw(t, "concat") for t in xs]
+        if axis not in (1, -3):
+            raise NotImplementedError("concat: only along the channel axis of NCHW maps")
+        if any((s[0], s[2], s[3]) != (shapes[0][0], shapes[0][2], shapes[0][3]) for s in shapes):
+            raise ValueError(f"concat: shape mismatch {shapes}")
+        n, _, h, w = shapes[0]
+        return self._emit("concat", list(xs), (n, sum(s[1] for s in shapes), h, w))
 
     def maxpool(self, x, k, stride, pad) -> SymTensor:
         n, c, h, w = _nchw(x, "MaxPool2d")

@@ -12,6 +12,8 @@ from .mobilenetv1 import MobileNetV1  # noqa: F401
 from .mobilenetv2 import MobileNetV2, mobilenet_v2  # noqa: F401
 from .darknet53 import DarkNet53, darknet53  # noqa: F401
 from .darknet import DarkNet  # noqa: F401
+from .det_mobilenet import MobileNet  # noqa: F401
+from .yolov3 import YOLOv3, YOLOv3FPN, YOLOv3Head, YoloDetBlock  # noqa: F401
 
 # name -> constructor, keyed like tlxcv_b200.testing.RECIPES / tests/golden
 REGISTRY = {
@@ -21,4 +23,5 @@ REGISTRY = {
     "resnext101_32x4d": resnext101_32x4d,
     "mobilenet_v1": MobileNetV1, "mobilenet_v2": mobilenet_v2,
     "darknet53_cls": darknet53, "darknet53_det": DarkNet,
+    "mobilenet_v1_det": MobileNet, "yolov3_darknet53": YOLOv3,
 }

@@ -22,14 +22,16 @@ from typing import Any
 from . import graph as _g
 
 # op kinds / activations / dtypes: keep in sync with include/tlxcv_b200.h
-OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW, OP_IMPORT_U8 = range(9)
+(OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW, OP_IMPORT_U8,
+ OP_UPSAMPLE_CONCAT) = range(10)
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY = range(4)
 DT_U8 = 4
 DT_F32, DT_BF16, DT_I64, DT_ACT = 0, 1, 2, 3          # DT_ACT: bf16 in the default mode, f32 in validation mode
 ROLE_INTERNAL, ROLE_INPUT, ROLE_OUTPUT = 0, 1, 2
 
 _ACT = {None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6, "leaky": ACT_LEAKY}
-OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw", "import_u8_nhwc"]
+OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw", "import_u8_nhwc",
+            "upsample_concat"]
 
 
 @dataclass
@@ -191,6 +193,37 @@ def lower(graph: _g.Graph) -> PlanSpec:
             out = new_tensor(graph.shapes[nd.out], DT_ACT)
             spec.ops.append(OpSpec(OP_IMPORT_U8, ins[0], out, conv=None, path=nd.path, norm=nd.module))
             gid2plan[nd.out] = out
+            produced_at[nd.out] = i
+            continue
+        if nd.op in ("upsample", "concat"):
+            # out[..., :C0] = in0 up-sampled r times, out[..., C0:] = in1 up-sampled s times (nearest): ONE pass writes the
+            # concatenated map.  `concat([upsample(route), x])` of YOLOv3FPN (detection/yolov3.py:244,252-253) is one op.
+            if nd.op == "upsample":
+                op = OpSpec(OP_UPSAMPLE_CONCAT, ins[0], -1, r=nd.attrs["scale"], s=1, path=nd.path)
+                cur = nd.out
+                j = sole_consumer(cur, "concat")
+                if j is not None and len(nodes[j].inputs) == 2:
+                    other = [t for t in nodes[j].inputs if t != cur]
+                    if len(other) == 1 and other[0] in produced_at and produced_at[other[0]] < i:
+                        if nodes[j].inputs[0] == cur:
+                            op.in1 = gid2plan[other[0]]
+                        else:       # the up-sampled map is the second part
+                            op.in0, op.in1, op.r, op.s = gid2plan[other[0]], ins[0], 1, nd.attrs["scale"]
+                        absorbed.add(j)
+                        cur = nodes[j].out
+                op.out = new_tensor(graph.shapes[cur], DT_ACT)
+                spec.ops.append(op)
+                gid2plan[cur] = op.out
+                produced_at[cur] = i
+                continue
+            acc = ins[0]
+            for k, nxt in enumerate(ins[1:]):       # more than two parts: pairwise, left to right
+                a, b = spec.tensors[acc], spec.tensors[nxt]
+                last = k == len(ins) - 2
+                out = new_tensor(graph.shapes[nd.out] if last else (a.n, a.c + b.c, a.h, a.w), DT_ACT)
+                spec.ops.append(OpSpec(OP_UPSAMPLE_CONCAT, acc, out, in1=nxt, r=1, s=1, path=nd.path))
+                acc = out
+            gid2plan[nd.out] = acc
             produced_at[nd.out] = i
             continue
         if nd.op == "bn":

@@ -49,6 +49,8 @@ RECIPES = {
     "mobilenet_v2": ("mobilenet_v2", 3.0),
     "darknet53_cls": ("darknet53_cls", 0.02),
     "darknet53_det": ("darknet53_det", 1.0),
+    "yolov3_darknet53": ("darknet53_det", 1.0),
+    "mobilenet_v1_det": ("mobilenet_v1", 1.0),
 }
 
 
@@ -117,6 +119,20 @@ def structured_images(n: int, size: int = 224, seed: int = INPUT_SEED, first: in
         wave = amp.view(3, 1, 1) * torch.sin(2 * math.pi * (fy * yy + fx * xx) + ph.view(3, 1, 1))
         out[i] = torch.randn(3, size, size, generator=g) * gain + off.view(3, 1, 1) + wave
     return out
+
+
+DICT_INPUT = ("darknet53_det", "yolov3_darknet53", "mobilenet_v1_det")     # forward takes {"images": NCHW}
+
+
+def model_input(name, x):
+    return {"images": x} if name in DICT_INPUT else x
+
+
+def flatten_outputs(y):
+    """Outputs of a forward as a flat list of tensors: a tensor, a list of maps, or YOLOv3's dict (body, neck, head order)."""
+    if isinstance(y, dict):
+        return [t for k in ("body_feats", "neck_feats", "yolo_head_outs") for t in y[k]]
+    return list(y) if isinstance(y, (list, tuple)) else [y]
 
 
 def parity_stats(y, ref):

@@ -37,7 +37,8 @@ def main():
     model = model.cuda().set_eval()
     x = synthetic_images(min(a.batch, 8), a.size).cuda()
     x = x.repeat((a.batch + x.shape[0] - 1) // x.shape[0], 1, 1, 1)[:a.batch].contiguous()
-    args = ({"images": x},) if a.model == "darknet53_det" else (x,)
+    from tlxcv_b200.testing import DICT_INPUT
+    args = ({"images": x},) if a.model in DICT_INPUT else (x,)
     plan, _, flat = runtime.get_plan(model, args, {})
     outs = plan.alloc_outputs()
     for _ in range(3):
