@@ -14,11 +14,13 @@
  *   MobileNetV1.forward classification/mobilenetv1.py:254-262       tlxcv_plan_run
  *   DarkNet.forward     detection/backbones/darknet.py:299-312      tlxcv_plan_run
  *   DarkNet.forward     classification/darknet53.py:100-133         tlxcv_plan_run
- *   ImageClassification.predict tasks/image_classification.py:20-23 tlxcv_plan_run (+ARGMAX op)
+ *   ImageClassification.predict tasks/image_classification.py:20-23 tlxcv_plan_run (+ARGMAX op, fused into the
+ *                                                                   Linear launch that produces the logits)
  *   nn.GroupConv2d + nn.BatchNorm2d + nn.ReLU/ReLU6/LeakyReLU + add TLXCV_OP_CONV
  *   nn.MaxPool2d                                                    TLXCV_OP_MAXPOOL
  *   nn.AdaptiveAvgPool2d(1)                                         TLXCV_OP_GAP
  *   nn.Linear                                                       TLXCV_OP_LINEAR
+ *   tlx.losses.softmax_cross_entropy_with_logits  tasks/image_classification.py:14  TLXCV_OP_SOFTMAX_CE
  *   Interpolater (nearest x2) + tlx.concat  detection/yolov3.py:244,252  TLXCV_OP_UPSAMPLE_CONCAT
  *   YOLOv3FPN / YOLOv3Head convs     detection/yolov3.py:122-258,306-378  TLXCV_OP_CONV (bias, any C_out)
  *   Module construction / set_eval (weights become static)          tlxcv_plan_build
@@ -78,9 +80,12 @@ typedef enum {
                                  (x - mean[c]) / std[c]: the reference's host-side Normalize + ToTensor
                                  (demo/image_classification/predict-resnet.py:50-54) fused into the layout
                                  pass; bn_mean / bn_var carry device pointers to float mean[C] / std[C]      */
-  TLXCV_OP_UPSAMPLE_CONCAT = 9 /* out[..., :C0] = in0 nearest-up-sampled r times, out[..., C0:] = in1 up-sampled s
+  TLXCV_OP_UPSAMPLE_CONCAT = 9, /* out[..., :C0] = in0 nearest-up-sampled r times, out[..., C0:] = in1 up-sampled s
                                  times (in1 = -1: up-sampling alone; r = s = 1: channel concat): Interpolater +
                                  tlx.concat of YOLOv3FPN.forward (detection/yolov3.py:244,252-253) in one pass          */
+  TLXCV_OP_SOFTMAX = 10,     /* (N, K) fp32 logits -> (N, K) fp32 probabilities (softmax over the class axis)           */
+  TLXCV_OP_SOFTMAX_CE = 11   /* in0 = (N, K) fp32 logits, in1 = (N) int64 labels -> (1) fp32 mean cross-entropy:
+                                 tlx.losses.softmax_cross_entropy_with_logits (tasks/image_classification.py:10-15)        */
 } tlxcv_op_kind;
 
 typedef enum { TLXCV_ACT_NONE = 0, TLXCV_ACT_RELU = 1, TLXCV_ACT_RELU6 = 2, TLXCV_ACT_LEAKY = 3 } tlxcv_act;

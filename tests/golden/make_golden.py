@@ -108,6 +108,14 @@ def main():
             **arrays,
         )
         print(fname, [tuple(o.shape) for o in outs], "std", float(outs[0].std()))
+    # OpenCV INTER_LINEAR vectors for oracle/cv_resize.py (the arithmetic behind tensorlayerx's Resize on numpy images)
+    import cv2
+    rng = np.random.default_rng(0)
+    vec = {"cv2_version": np.array(cv2.__version__)}
+    for k, (hs, ws, h, w) in enumerate([(37, 53, 64, 96), (120, 90, 32, 32), (17, 9, 5, 3), (48, 64, 224, 224), (31, 31, 31, 31)]):
+        img = rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+        vec[f"src{k}"], vec[f"dst{k}"] = img, cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR)
+    np.savez_compressed(os.path.join(out_dir, "cv_resize.npz"), **vec)
     with open(os.path.join(out_dir, "manifests.json"), "w") as f:
         json.dump(manifests, f)
     print("wrote", out_dir)

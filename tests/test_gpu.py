@@ -769,3 +769,73 @@ def test_upsample_concat_orders():
     up = torch.nn.functional.interpolate(ya, scale_factor=2.0)
     assert torch.equal(o1, torch.cat([up, yb], 1)) and torch.equal(o2, torch.cat([yb, up], 1))
     assert torch.equal(o3, torch.cat([yb, yb, yb], 1))
+
+
+def test_softmax_cross_entropy_argmax_heads():
+    """tasks/image_classification.py:10-23 on the device: loss_fn = mean softmax cross-entropy of the fp32 logits, predict =
+    argmax fused into the Linear launch (64-bit atomicMax keys, decoded by the last CTA; the logits are not even written when
+    nothing else reads them), plus tlx.softmax; all against torch on the same logits."""
+    import tlxcv_b200 as tlx
+    from tlxcv_b200 import models, nn, tasks
+    from tlxcv_b200.testing import seeded_state_dict, structured_images
+
+    m = models.resnet18()
+    m.load_state_dict(seeded_state_dict(m.state_dict(), "resnet18", fc_gain=3.0))     # spread logits: a non-trivial softmax
+    m = m.cuda().set_eval()
+    task = tasks.ImageClassification(m)
+    x = structured_images(150, 64).cuda()                                             # 150 rows: two M tiles, the second ragged
+    y = torch.randint(0, 1000, (150,), generator=torch.Generator().manual_seed(1)).cuda()
+    logits = m(x)
+    pred = task.predict(x)
+    assert pred.dtype == torch.int64 and torch.equal(pred, logits.argmax(1))
+    plan = next(iter(task._predictor.__dict__["_b200_plans"].values()))[0]
+    kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
+    assert any(k.endswith("+argmax") for k in kernels) and "argmax_rows" not in kernels, kernels
+    for _ in range(3):                                                                # keys / ticket are left clean for the next launch
+        assert torch.equal(task.predict(x), pred)
+    loss = task.loss_fn(logits, y)
+    want = torch.nn.functional.cross_entropy(logits, y)
+    assert loss.shape == () and abs(float(loss) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+
+    class Eval(nn.Module):
+        def __init__(self, task):
+            super().__init__()
+            self.task = task
+
+        def forward(self, images, labels):
+            out = self.task.backbone(images)
+            return self.task.loss_fn(out, labels), tlx.argmax(out, axis=-1), tlx.softmax(out), out
+
+    loss2, pred2, prob, out = Eval(task).set_eval()(x, y)
+    assert torch.equal(out, logits) and torch.equal(pred2, pred)
+    assert abs(float(loss2) - float(want)) <= 1e-5 * max(1.0, abs(float(want)))
+    assert float((prob - torch.softmax(logits, 1)).abs().max()) <= 1e-6 and float((prob.sum(1) - 1).abs().max()) <= 1e-5
+    # fp32 validation mode: stand-alone argmax kernel, same answers
+    from tlxcv_b200 import runtime
+    plan32, _, flat = runtime.get_plan(task._predictor, (x,), {}, precision=runtime.PREC_F32)
+    logits32 = runtime.get_plan(m, (x,), {}, precision=runtime.PREC_F32)[0].run([x], graph=False)[0]
+    assert torch.equal(plan32.run(flat, graph=False)[0], logits32.argmax(1))
+
+
+@pytest.mark.parametrize("hs,ws,size", [(375, 500, 224), (100, 133, 224), (224, 224, 224), (300, 200, 96)])
+def test_resize_normalize_totensor_fused_into_the_input_kernel(hs, ws, size):
+    """Resize((H, W)) + Normalize(mean, std) + ToTensor of the reference's predict demos
+    (demo/image_classification/predict-resnet.py:50-56) in ONE input pass: bit-identical logits to resizing every image on
+    the host with the oracle restatement of cv2 INTER_LINEAR (integer work: exact), normalising it and feeding fp32 NCHW."""
+    from oracle.cv_resize import resize_u8
+    from tlxcv_b200 import models, vision
+    from tlxcv_b200.testing import seeded_state_dict
+
+    mean, std = (125.31, 122.95, 113.86), (62.99, 62.09, 66.70)
+    backbone = models.resnet18()
+    backbone.load_state_dict(seeded_state_dict(backbone.state_dict(), "resnet18"))
+    net = vision.Preprocessed(backbone, mean, std, resize=(size, size)).cuda().set_eval()
+    u8 = torch.randint(0, 256, (3, hs, ws, 3), generator=torch.Generator().manual_seed(hs + ws), dtype=torch.uint8)
+    resized = torch.from_numpy(np.stack([resize_u8(img.numpy(), size, size) for img in u8]))
+    x = ((resized.float() - torch.tensor(mean)) / torch.tensor(std)).permute(0, 3, 1, 2).contiguous()
+    y_fused = net(u8.cuda()).cpu()
+    y_host = backbone(x.cuda()).cpu()
+    assert torch.equal(y_fused, y_host)
+    plan = next(iter(net.__dict__["_b200_plans"].values()))[0]
+    k0 = plan.op_info(0)["kernel"]
+    assert k0.startswith("import_u8_resize") if (hs, ws) != (size, size) else k0.startswith("import_u8_nhwc"), k0

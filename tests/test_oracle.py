@@ -131,3 +131,22 @@ def test_recipe_keeps_logits_small(manifests):
     y = restated.forward("resnet18", sd, synthetic_images(2, 96))
     assert 0.05 < float(y.std()) < 1.0
     assert torch.isfinite(y).all()
+
+
+def test_cv_resize_restatement_against_opencv_vectors_and_live(golden_dir):
+    """oracle/cv_resize.py (the Resize of the reference's transform pipeline = cv2 INTER_LINEAR on uint8) against vectors
+    minted from cv2, and against cv2 itself where it imports."""
+    from oracle.cv_resize import resize_u8
+
+    g = np.load(os.path.join(golden_dir, "cv_resize.npz"))
+    k = 0
+    while f"src{k}" in g.files:
+        src, dst = g[f"src{k}"], g[f"dst{k}"]
+        assert np.array_equal(resize_u8(src, dst.shape[0], dst.shape[1]), dst), k
+        k += 1
+    assert k >= 5
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(11)
+    for hs, ws, h, w in [(375, 500, 224, 224), (100, 133, 224, 224), (300, 200, 608, 608), (64, 64, 64, 64), (2, 2, 7, 5)]:
+        img = rng.integers(0, 256, (hs, ws, 3), dtype=np.uint8)
+        assert np.array_equal(resize_u8(img, h, w), cv2.resize(img, (w, h), interpolation=cv2.INTER_LINEAR))

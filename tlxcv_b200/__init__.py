@@ -86,6 +86,24 @@ def concat(values, axis=0):
     return _traced(values[0], "concat").concat(values, axis)
 
 
+def softmax(logits, axis=-1):
+    """``tlx.softmax`` over the class axis of the fp32 logits (the "final FC + softmax" of the north star)."""
+    return _traced(logits, "softmax").softmax(logits, axis)
+
+
+class _Losses:
+    """``tensorlayerx.losses`` (only what ``ImageClassification.loss_fn`` uses, tasks/image_classification.py:10-15)."""
+
+    @staticmethod
+    def softmax_cross_entropy_with_logits(output, target, reduction="mean"):
+        if reduction != "mean":
+            raise NotImplementedError("softmax_cross_entropy_with_logits: only reduction='mean'")
+        return _traced(output, "losses.softmax_cross_entropy_with_logits").softmax_ce(output, target)
+
+
+losses = _Losses()
+
+
 def get_tensor_shape(x):
     return list(x.shape)
 

@@ -200,6 +200,7 @@ struct EpiArgs {
   const float* scale;
   const float* shift;
   float* out_f32;
+  unsigned long long* amax_keys;
   const CUtensorMap* tmap_out;
   const CUtensorMap* tmap_res;
   int M, Cout, n_tiles, num_tiles, first_tile, tile_stride;
@@ -449,7 +450,22 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       }
       if (F32) {
         const int gr = m0 + lane;
-        if (gr < a.M) {
+        if (gr < a.M && a.amax_keys != nullptr) {
+          // fused argmax (tlx.argmax of ImageClassification.predict): best of this lane's 32 columns, first index on ties
+          float best = -3.402823466e38f;
+          int bi = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float v = __uint_as_float(static_cast<uint32_t>(pr[j >> 1] >> ((j & 1) * 32)));
+            if (cbase + j < a.Cout && v > best) best = v, bi = j;
+          }
+          if (cbase < a.Cout) {
+            const uint32_t fb = __float_as_uint(best);
+            const uint32_t ord = (fb & 0x80000000u) ? ~fb : (fb | 0x80000000u);  // unsigned order == float order
+            atomicMax(a.amax_keys + gr, (static_cast<unsigned long long>(ord) << 32) | (0xffffffffu - static_cast<uint32_t>(cbase + bi)));
+          }
+        }
+        if (gr < a.M && a.out_f32 != nullptr) {
           float* dst = a.out_f32 + static_cast<size_t>(gr) * a.Cout + cbase;
           if ((a.Cout & 3) == 0) {
 #pragma unroll
@@ -794,6 +810,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     a.cpw = max(1, (BLOCK_N / 32) / (epi_warps / 4));
     a.scale = p.scale, a.shift = p.shift;
     a.out_f32 = reinterpret_cast<float*>(p.out);
+    a.amax_keys = p.amax_keys;
     a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
     a.M = p.M, a.Cout = p.Cout, a.n_tiles = p.n_tiles, a.num_tiles = num_tiles;
     a.first_tile = worker, a.tile_stride = n_workers;
@@ -908,6 +925,26 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       tmem_dealloc_2sm<kTmemColsK>(tmem_base);
     else
       tmem_dealloc<kTmemColsK>(tmem_base);
+  }
+  if (!TWO && !DUAL && p.amax_keys != nullptr) {
+    // fused argmax: the last CTA to get here decodes every row's key and leaves keys / ticket zero for the next launch
+    // (the flag lives in the spare tail of the barrier block: a static __shared__ variable would push the kernel past
+    // the 227 KB it already requests dynamically)
+    volatile uint32_t* last_cta = reinterpret_cast<volatile uint32_t*>(bars + 120);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      *last_cta = atomicAdd(p.amax_ticket, 1u) == gridDim.x - 1 ? 1u : 0u;
+    }
+    __syncthreads();
+    if (*last_cta) {
+      __threadfence();
+      for (int r = threadIdx.x; r < p.M; r += blockDim.x) {
+        const unsigned long long key = __ldcg(p.amax_keys + r);
+        p.amax_out[r] = static_cast<long long>(0xffffffffu - static_cast<uint32_t>(key));
+        p.amax_keys[r] = 0ull;
+      }
+      if (threadIdx.x == 0) *p.amax_ticket = 0u;
+    }
   }
 }
 

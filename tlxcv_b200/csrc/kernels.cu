@@ -187,6 +187,44 @@ __global__ void import_u8_rgb_x4_kernel(const uint8_t* __restrict__ src, uint4* 
   dst[idx * 2 + 1] = o1;
 }
 
+// uint8 NHWC (N, Hs, Ws, C <= 4) -> bilinear resize to (H, W) -> (x - mean) / std -> [N][H][Wp][4] activations: the reference's
+// Resize + Normalize + ToTensor (demo/image_classification/predict-resnet.py:50-54) in the plan's input pass.  The resize
+// is OpenCV's INTER_LINEAR for 8-bit images bit for bit (what tensorlayerx's Resize runs on a numpy image): 11-bit
+// fixed-point weights from the host-built tables `tx` / `ty` = {i0, i1, c0, c1} per destination column / row,
+//   D = S[i0] * c0 + S[i1] * c1  (horizontal, 32 bit),  dst = ((b0 * (D0 >> 4) >> 16) + (b1 * (D1 >> 4) >> 16) + 2) >> 2.
+template <typename T>
+__global__ void import_u8_resize_kernel(const uint8_t* __restrict__ src, T* __restrict__ dst, const float* __restrict__ mean,
+                                        const float* __restrict__ stdv, const int4* __restrict__ tx, const int4* __restrict__ ty,
+                                        int C, int Hs, int Ws, int H, int W, int Wp, int pad_l, size_t total) {
+  pdl_wait();
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int xp = static_cast<int>(idx % Wp);
+  const size_t row = idx / Wp;
+  const int y = static_cast<int>(row % H);
+  const size_t n = row / H;
+  const int x = xp - pad_l;
+  float v[4] = {0.f, 0.f, 0.f, 0.f};
+  if (x >= 0 && x < W) {
+    const int4 cx = __ldg(tx + x), cy = __ldg(ty + y);
+    const uint8_t* r0 = src + (n * Hs + cy.x) * static_cast<size_t>(Ws) * C;
+    const uint8_t* r1 = src + (n * Hs + cy.y) * static_cast<size_t>(Ws) * C;
+    for (int c = 0; c < C; ++c) {
+      const int d0 = r0[cx.x * C + c] * cx.z + r0[cx.y * C + c] * cx.w;
+      const int d1 = r1[cx.x * C + c] * cx.z + r1[cx.y * C + c] * cx.w;
+      int o = (((cy.z * (d0 >> 4)) >> 16) + ((cy.w * (d1 >> 4)) >> 16) + 2) >> 2;
+      o = min(max(o, 0), 255);
+      v[c] = (static_cast<float>(o) - __ldg(mean + c)) / __ldg(stdv + c);
+    }
+  }
+  T* d = dst + idx * 4;
+  if constexpr (sizeof(T) == 2) {
+    *reinterpret_cast<uint2*>(d) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+  } else {
+    *reinterpret_cast<float4*>(d) = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
 // general transpose [N][C][HW] fp32 -> [N][HW][C] T through a 32x32 smem tile
 template <typename T>
 __global__ void import_nchw_tile_kernel(const float* __restrict__ src, T* __restrict__ dst, int C, int HW) {
@@ -580,6 +618,75 @@ __global__ void argmax_rows_kernel(const float* __restrict__ logits, long long* 
   if (lane == 0) dst[row] = besti;
 }
 
+// Row-wise softmax of fp32 logits, one warp per row: max and sum by warp shuffles, exp of the shifted logits
+// (tlx.softmax(logits, axis=-1); the "final FC + softmax" of the north star).
+__global__ void softmax_rows_kernel(const float* __restrict__ logits, float* __restrict__ dst, int N, int K) {
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= N) return;
+  const float* p = logits + static_cast<size_t>(row) * K;
+  float mx = -FLT_MAX;
+  for (int i = lane; i < K; i += 32) mx = fmaxf(mx, p[i]);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+  float sum = 0.0f;
+  for (int i = lane; i < K; i += 32) sum += expf(p[i] - mx);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+  const float inv = 1.0f / sum;
+  float* d = dst + static_cast<size_t>(row) * K;
+  for (int i = lane; i < K; i += 32) d[i] = expf(p[i] - mx) * inv;
+}
+
+// Mean softmax cross-entropy of fp32 logits against int64 class labels (tlx.losses.softmax_cross_entropy_with_logits,
+// tasks/image_classification.py:10-15): one warp per row writes  log(sum exp(l - max)) + max - l[target]  into a scratch
+// row, the LAST block to finish (ticket counter, reset for the next launch) sums the rows in index order - so the result
+// does not depend on block scheduling - and writes the mean.  A label outside [0, K) gives NaN.
+__global__ void softmax_ce_kernel(const float* __restrict__ logits, const long long* __restrict__ target, float* __restrict__ row_loss,
+                                  unsigned int* __restrict__ ticket, float* __restrict__ dst, int N, int K) {
+  pdl_wait();
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row < N) {
+    const float* p = logits + static_cast<size_t>(row) * K;
+    float mx = -FLT_MAX;
+    for (int i = lane; i < K; i += 32) mx = fmaxf(mx, p[i]);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, off));
+    float sum = 0.0f;
+    for (int i = lane; i < K; i += 32) sum += expf(p[i] - mx);
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, off);
+    if (lane == 0) {
+      const long long t = target[row];
+      row_loss[row] = (t >= 0 && t < K) ? logf(sum) + mx - p[t] : __int_as_float(0x7fc00000);
+    }
+  }
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  if (threadIdx.x < 32) {
+    float acc = 0.0f;
+    for (int base = 0; base < N; base += 32) {  // fixed order: lanes over 32 consecutive rows, then a shuffle tree
+      float v = base + lane < N ? __ldcg(row_loss + base + lane) : 0.0f;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      acc += v;
+    }
+    if (lane == 0) {
+      dst[0] = acc / static_cast<float>(N);
+      *ticket = 0;
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // fp32 direct convolution (validation mode): thread = (pixel, 4 output channels)
 // weights [R][S][C/g][K]; lanes run along K so weight loads coalesce and input loads broadcast
@@ -689,6 +796,17 @@ cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, con
     TLXCV_LAUNCH(import_u8_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, src, static_cast<float*>(dst), mean, stdv, C, H, W, Wp, pad_l, total);
   else
     TLXCV_LAUNCH(import_u8_nhwc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, src, static_cast<__nv_bfloat16*>(dst), mean, stdv, C, H, W, Wp, pad_l, total);
+  return cudaGetLastError();
+}
+
+cudaError_t import_u8_resize(const uint8_t* src, void* dst, const float* mean, const float* stdv, const int4* tx, const int4* ty,
+                             int N, int C, int Hs, int Ws, int H, int W, int Wp, int pad_l, int is_f32, cudaStream_t st) {
+  if (C > 4) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * H * Wp;
+  if (is_f32)
+    TLXCV_LAUNCH(import_u8_resize_kernel<float>, blocks_for(total), kThreads, 0, st, src, static_cast<float*>(dst), mean, stdv, tx, ty, C, Hs, Ws, H, W, Wp, pad_l, total);
+  else
+    TLXCV_LAUNCH(import_u8_resize_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, src, static_cast<__nv_bfloat16*>(dst), mean, stdv, tx, ty, C, Hs, Ws, H, W, Wp, pad_l, total);
   return cudaGetLastError();
 }
 
@@ -910,6 +1028,20 @@ cudaError_t upsample_concat(const void* a, const void* b, void* dst, int N, int 
 cudaError_t argmax_rows(const float* logits, long long* dst, int N, int K, cudaStream_t st) {
   const int warps_per_block = 8;
   TLXCV_LAUNCH(argmax_rows_kernel, (N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st, logits, dst, N, K);
+  return cudaGetLastError();
+}
+
+cudaError_t softmax_rows(const float* logits, float* dst, int N, int K, cudaStream_t st) {
+  const int warps_per_block = 8;
+  TLXCV_LAUNCH(softmax_rows_kernel, (N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st, logits, dst, N, K);
+  return cudaGetLastError();
+}
+
+cudaError_t softmax_ce(const float* logits, const long long* target, float* row_loss, unsigned int* ticket, float* dst, int N, int K,
+                       cudaStream_t st) {
+  const int warps_per_block = 8;
+  TLXCV_LAUNCH(softmax_ce_kernel, (N + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st, logits, target, row_loss,
+               ticket, dst, N, K);
   return cudaGetLastError();
 }
 

@@ -54,6 +54,12 @@ struct ConvKernelParams {
   const float* scale2;
   const float* shift2;
   unsigned long long* trace;  // debug: TLXCV_DEBUG_TRACE_CONV timeline buffer (NULL in normal operation)
+  // argmax over the output channels fused into an fp32-output (Linear) launch: every epilogue thread folds its 32 columns
+  // into amax_keys[row] with one 64-bit atomicMax of (order-preserving float bits << 32 | ~column), the last CTA to finish
+  // decodes the keys into amax_out[row] (first maximal index, like torch.argmax) and resets keys and ticket for the next launch
+  unsigned long long* amax_keys;
+  long long* amax_out;
+  unsigned int* amax_ticket;
 };
 
 struct TcConvLaunch {
@@ -185,6 +191,9 @@ cudaError_t export_nchw(const void* src, float* dst, int N, int C, int Cs, int H
 // NHWC uint8 (C <= 4) -> [N][H][Wp][4] activations, (x - mean[c]) / std[c]; Wp == W, pad_l == 0 for the dense layout
 cudaError_t import_u8_nhwc(const uint8_t* src, void* dst, const float* mean, const float* stdv, int N, int C, int H, int W,
                            int Wp, int pad_l, int is_f32, cudaStream_t st);
+// the same with OpenCV's 8-bit INTER_LINEAR resize (Hs, Ws) -> (H, W) in front; tx[W] / ty[H] = {i0, i1, c0, c1} (resize_tables)
+cudaError_t import_u8_resize(const uint8_t* src, void* dst, const float* mean, const float* stdv, const int4* tx, const int4* ty,
+                             int N, int C, int Hs, int Ws, int H, int W, int Wp, int pad_l, int is_f32, cudaStream_t st);
 cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad,
                          int is_f32, cudaStream_t st);
 cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st);
@@ -193,6 +202,12 @@ cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const flo
                         int act1, float alpha1, int act2, float alpha2, int is_f32, cudaStream_t st);
 cudaError_t add_act(const void* a, const void* b, void* dst, size_t n, int act, float alpha, int is_f32, cudaStream_t st);
 cudaError_t argmax_rows(const float* logits, long long* dst, int N, int K, cudaStream_t st);
+// probabilities of fp32 logits (N, K), row-wise
+cudaError_t softmax_rows(const float* logits, float* dst, int N, int K, cudaStream_t st);
+// mean softmax cross-entropy of (N, K) fp32 logits against int64 labels -> dst[0]; row_loss: N floats of scratch, ticket: one
+// zero-initialised counter (the kernel leaves it zero)
+cudaError_t softmax_ce(const float* logits, const long long* target, float* row_loss, unsigned int* ticket, float* dst, int N, int K,
+                       cudaStream_t st);
 // dst[N][H][W][C0 + C1]: channels [0, C0) = a nearest-up-sampled ra times, [C0, C0 + C1) = b up-sampled rb times (b may be NULL)
 cudaError_t upsample_concat(const void* a, const void* b, void* dst, int N, int H, int W, int C0, int C1, int ra, int rb,
                             int is_f32, cudaStream_t st);

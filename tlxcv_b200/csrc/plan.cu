@@ -2,6 +2,7 @@
 // weight packing, BN folding, kernel/tile selection, TMA descriptors), plan run (stream launch or
 // CUDA-graph replay), host-buffer run, per-op profiling.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -31,7 +32,7 @@ struct TensorRt {
 };
 
 enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
-                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat };
+                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat, kImplSoftmax, kImplSoftmaxCe };
 
 struct OpRt {
   tlxcv_op_desc d;
@@ -45,6 +46,13 @@ struct OpRt {
   bool nop = false;           // fused into another op: no launch, no tensors of its own
   int dual_a = -1;            // index of the 1x1 conv whose output was this conv's residual and now runs as the
                               // first accumulator of this op's dual-GEMM kernel (-1: none)
+  int fused_argmax = -1;      // Linear: index of the ARGMAX op over its logits that runs inside this launch (-1: none)
+  bool skip_logits = false;   // ... and nothing else reads the logits: they are never written
+  unsigned long long* amax_keys = nullptr;  // fused argmax scratch (owned, zero between launches)
+  unsigned int* ticket = nullptr;           // fused argmax / softmax-CE "last block" counter (owned, zero between launches)
+  float* row_loss = nullptr;                // softmax-CE per-row scratch (owned)
+  int4* resize_tx = nullptr;                // import_u8 with a resize in front: per-column / per-row {i0, i1, c0, c1} (owned)
+  int4* resize_ty = nullptr;
   float* scale2 = nullptr;    // folded BN of this op's own (second) GEMM in a dual launch (owned)
   float* shift2 = nullptr;
   void* weights = nullptr;    // packed weights (owned)
@@ -208,6 +216,25 @@ void set_info(OpRt& op, const char* kernel, int launches, int bound, double flop
   snprintf(op.info.kernel, sizeof op.info.kernel, "%s", kernel);
   op.info.launches = launches, op.info.bound = bound, op.info.flops = flops, op.info.bytes = bytes;
   op.info.grid = grid, op.info.block = block, op.info.smem_bytes = smem, op.info.tile_n = tile_n;
+}
+
+// OpenCV's INTER_LINEAR coefficient set-up for 8-bit images (imgproc/src/resize.cpp): source indices and 11-bit weights per
+// destination index.  Columns clamp the FRACTION at the image border, rows clamp the source INDICES (oracle/cv_resize.py).
+std::vector<int4> resize_table(int dst, int src, bool clamp_fraction) {
+  std::vector<int4> t(dst);
+  const double scale = 1.0 / (static_cast<double>(dst) / static_cast<double>(src));
+  for (int d = 0; d < dst; ++d) {
+    float f = static_cast<float>((d + 0.5) * scale - 0.5);
+    int s = static_cast<int>(std::floor(f));
+    f -= static_cast<float>(s);
+    if (clamp_fraction) {
+      if (s < 0) f = 0.0f, s = 0;
+      if (s >= src - 1) f = 0.0f, s = src - 1;
+    }
+    const int c0 = static_cast<int>(std::nearbyintf((1.0f - f) * 2048.0f)), c1 = static_cast<int>(std::nearbyintf(f * 2048.0f));
+    t[d] = make_int4(std::min(std::max(s, 0), src - 1), std::min(std::max(s + 1, 0), src - 1), c0, c1);
+  }
+  return t;
 }
 
 // C_in <= 4 stem on the row-ring kernel (stem_rowring.cu); `out` is the pooled map when a max-pool is fused
@@ -466,6 +493,11 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
         TLX_CUDA(ctx, import_nchw(static_cast<const float*>(pin), pout, in.d.n, in.d.c, in.d.h, in.d.w, out.cs, is_f32, st));
       break;
     case kImplImportU8:
+      if (op.resize_tx != nullptr) {
+        TLX_CUDA(ctx, import_u8_resize(static_cast<const uint8_t*>(pin), pout, d.bn_mean, d.bn_var, op.resize_tx, op.resize_ty, in.d.n,
+                                       in.d.c, in.d.h, in.d.w, out.d.h, out.d.w, out.wp > 0 ? out.wp : out.d.w, out.pad_l, is_f32, st));
+        break;
+      }
       TLX_CUDA(ctx, import_u8_nhwc(static_cast<const uint8_t*>(pin), pout, d.bn_mean, d.bn_var, in.d.n, in.d.c, in.d.h, in.d.w,
                                    out.wp > 0 ? out.wp : out.d.w, out.pad_l, is_f32, st));
       break;
@@ -480,7 +512,12 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
       break;
     case kImplTcConv: {
       TcConvLaunch L = op.tc;
-      L.p.out = pout;  // only read by fp32-output (logits) launches; bf16 tensors go through the baked TMA maps
+      L.p.out = op.skip_logits ? nullptr : pout;  // only read by fp32-output (logits) launches; bf16 tensors go through the baked TMA maps
+      if (op.fused_argmax >= 0) {
+        L.p.amax_keys = op.amax_keys, L.p.amax_ticket = op.ticket;
+        L.p.amax_out = static_cast<long long*>(tensor_ptr(p, p->ops[op.fused_argmax].d.out, inputs, outputs));
+        if (!L.p.amax_out) return fail(ctx, TLXCV_ERR_INVALID, "NULL external tensor pointer");
+      }
       TLX_CUDA(ctx, tc_conv_launch(L, st));
       break;
     }
@@ -509,6 +546,13 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
     case kImplUpsampleConcat:
       TLX_CUDA(ctx, upsample_concat(pin, pres, pout, out.d.n, out.d.h, out.d.w, in.d.c, d.in1 >= 0 ? p->tensors[d.in1].d.c : 0, d.r,
                                     d.s, is_f32, st));
+      break;
+    case kImplSoftmax:
+      TLX_CUDA(ctx, softmax_rows(static_cast<const float*>(pin), static_cast<float*>(pout), in.d.n, in.d.c, st));
+      break;
+    case kImplSoftmaxCe:
+      TLX_CUDA(ctx, softmax_ce(static_cast<const float*>(pin), static_cast<const long long*>(pres), op.row_loss, op.ticket,
+                               static_cast<float*>(pout), in.d.n, in.d.c, st));
       break;
     case kImplArgmax:
       TLX_CUDA(ctx, argmax_rows(static_cast<const float*>(pin), static_cast<long long*>(pout), in.d.n, in.d.c, st));
@@ -564,7 +608,8 @@ int capture_range(tlxcv_plan* p, int begin, int end, const void* const* inputs, 
 
 bool touches_external(const tlxcv_plan* p, const OpRt& op) {
   if (op.nop) return false;
-  for (int t : {op.d.in0, op.d.in1, op.d.out})
+  const int extra_out = op.fused_argmax >= 0 ? p->ops[op.fused_argmax].d.out : -1;
+  for (int t : {op.d.in0, op.d.in1, op.d.out, extra_out})
     if (t >= 0 && p->tensors[t].d.role != TLXCV_ROLE_INTERNAL) return true;
   return false;
 }
@@ -753,11 +798,39 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       B.d.in1 = -1;
     }
   }
+  // ---- pre-pass: `argmax(linear(x))` (ImageClassification.predict, tasks/image_classification.py:20-23): the argmax runs
+  //      inside the Linear launch (per-row 64-bit atomicMax keys, decoded by the last CTA); logits nobody else reads are
+  //      never written ----
+  if (!p->f32 && !tuning_env("TLXCV_NO_ARGMAX_FUSION")) {
+    for (int i = 0; i < n_ops; ++i) {
+      OpRt& A = p->ops[i];
+      if (A.nop || A.d.kind != TLXCV_OP_ARGMAX) continue;
+      const TensorRt& L = p->tensors[A.d.in0];
+      if (L.d.dtype != TLXCV_F32 || p->tensors[A.d.out].d.dtype != TLXCV_I64) continue;
+      int producer = -1, users = 0;
+      for (int k = 0; k < n_ops; ++k) {
+        if (p->ops[k].nop) continue;
+        if (p->ops[k].d.out == A.d.in0) producer = k;
+        if (p->ops[k].d.in0 == A.d.in0 || p->ops[k].d.in1 == A.d.in0) ++users;
+      }
+      if (producer < 0 || producer >= i || p->ops[producer].d.kind != TLXCV_OP_LINEAR || p->ops[producer].fused_argmax >= 0) continue;
+      p->ops[producer].fused_argmax = i;
+      p->ops[producer].skip_logits = users == 1 && L.d.role == TLXCV_ROLE_INTERNAL;
+      if (p->ops[producer].skip_logits) p->tensors[A.d.in0].elided = true;
+      A.nop = true;
+    }
+  }
   for (int i = 0; i < n_ops; ++i) {
     OpRt& op = p->ops[i];
     const tlxcv_op_desc& d = op.d;
     if (op.nop) continue;
     const int extra_in = op.dual_a >= 0 ? p->ops[op.dual_a].d.in0 : -1;
+    if (op.fused_argmax >= 0) {  // the fused argmax's result is written by this op
+      TensorRt& ao = p->tensors[p->ops[op.fused_argmax].d.out];
+      if (ao.first_def >= 0 || ao.d.role == TLXCV_ROLE_INPUT) return fail(ctx, TLXCV_ERR_INVALID, "op %d: tensor is written twice", i);
+      ao.first_def = i;
+      ao.last_use = std::max(ao.last_use, i);
+    }
     for (int t : {d.in0, d.in1, extra_in}) {
       if (t < 0) continue;
       if (p->tensors[t].d.role != TLXCV_ROLE_INPUT && p->tensors[t].first_def < 0)
@@ -777,6 +850,10 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       if (p->ops[i].nop) continue;
       TensorRt& o = p->tensors[p->ops[i].d.out];
       if (o.d.role == TLXCV_ROLE_INTERNAL) o.offset = arena.alloc(o.bytes);
+      if (p->ops[i].fused_argmax >= 0) {
+        TensorRt& ao = p->tensors[p->ops[p->ops[i].fused_argmax].d.out];
+        if (ao.d.role == TLXCV_ROLE_INTERNAL) ao.offset = arena.alloc(ao.bytes);
+      }
       const int extra_in = p->ops[i].dual_a >= 0 ? p->ops[p->ops[i].dual_a].d.in0 : -1;
       for (int t : {p->ops[i].d.in0, p->ops[i].d.in1, extra_in, p->ops[i].d.out}) {
         if (t < 0) continue;
@@ -803,7 +880,9 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     int rc = TLXCV_OK;
     if (op.nop) {
       op.impl = kImplNop;
-      set_info(op, d.kind == TLXCV_OP_CONV ? "(first GEMM of the dual conv)" : "(fused into the stem conv)", 0, 0, 0, 0, 0, 0, 0, 0);
+      set_info(op, d.kind == TLXCV_OP_CONV ? "(first GEMM of the dual conv)"
+                                           : (d.kind == TLXCV_OP_ARGMAX ? "(fused into the linear launch)" : "(fused into the stem conv)"),
+               0, 0, 0, 0, 0, 0, 0, 0);
       continue;
     }
     switch (d.kind) {
@@ -819,6 +898,18 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
             in.d.c > 4 || in.d.c != o.d.c || o.cs != 4 || !d.bn_mean || !d.bn_var)
           return fail(ctx, TLXCV_ERR_INVALID, "op %d: import_u8 expects external uint8 NHWC (C <= 4) + mean/std -> internal activation", i);
         op.impl = kImplImportU8;
+        if (in.d.n != o.d.n) return fail(ctx, TLXCV_ERR_INVALID, "op %d: import_u8 batch size mismatch", i);
+        if (in.d.h != o.d.h || in.d.w != o.d.w) {  // Resize((H, W)) in front of Normalize: fused into the same pass
+          if (in.d.h < 1 || in.d.w < 1) return fail(ctx, TLXCV_ERR_INVALID, "op %d: empty source image", i);
+          const std::vector<int4> tx = resize_table(o.d.w, in.d.w, true), ty = resize_table(o.d.h, in.d.h, false);
+          if ((rc = dev_alloc(p, &op.resize_tx, tx.size())) != TLXCV_OK) break;
+          if ((rc = dev_alloc(p, &op.resize_ty, ty.size())) != TLXCV_OK) break;
+          TLX_CUDA(ctx, cudaMemcpyAsync(op.resize_tx, tx.data(), tx.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+          TLX_CUDA(ctx, cudaMemcpyAsync(op.resize_ty, ty.data(), ty.size() * sizeof(int4), cudaMemcpyHostToDevice, st));
+          TLX_CUDA(ctx, cudaStreamSynchronize(st));  // the host tables go out of scope here
+          set_info(op, o.wp > 0 ? "import_u8_resize_padded" : "import_u8_resize", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+          break;
+        }
         set_info(op, o.wp > 0 ? "import_u8_nhwc_padded" : "import_u8_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_EXPORT_NCHW:
@@ -835,6 +926,30 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_F32 || in.d.h != 1 || in.d.w != 1)
           return fail(ctx, TLXCV_ERR_INVALID, "op %d: linear expects (N, F) activation -> (N, K) f32", i);
         rc = compile_conv(p, op, st, true);
+        if (rc == TLXCV_OK && op.fused_argmax >= 0) {
+          if (op.impl != kImplTcConv || op.tc.two || op.tc.dual) return fail(ctx, TLXCV_ERR_INVALID, "op %d: argmax fusion needs the single-CTA tcgen05 Linear", i);
+          if ((rc = dev_alloc(p, &op.amax_keys, static_cast<size_t>(in.d.n))) != TLXCV_OK) break;
+          if ((rc = dev_alloc(p, &op.ticket, 1)) != TLXCV_OK) break;
+          TLX_CUDA(ctx, cudaMemsetAsync(op.amax_keys, 0, std::max<size_t>(in.d.n * sizeof(unsigned long long), 256), st));
+          TLX_CUDA(ctx, cudaMemsetAsync(op.ticket, 0, 256, st));
+          snprintf(op.info.kernel + strlen(op.info.kernel), sizeof op.info.kernel - strlen(op.info.kernel), "+argmax");
+        }
+        break;
+      case TLXCV_OP_SOFTMAX:
+        if (in.d.dtype != TLXCV_F32 || o.d.dtype != TLXCV_F32 || o.d.n != in.d.n || o.d.c != in.d.c || in.d.h != 1 || in.d.w != 1)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: softmax expects (N, K) f32 -> (N, K) f32", i);
+        op.impl = kImplSoftmax;
+        set_info(op, "softmax_rows", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_SOFTMAX_CE:
+        if (d.in1 < 0 || in.d.dtype != TLXCV_F32 || p->tensors[d.in1].d.dtype != TLXCV_I64 || o.d.dtype != TLXCV_F32 ||
+            p->tensors[d.in1].d.n != in.d.n || o.d.n * o.d.c != 1 || in.d.h != 1 || in.d.w != 1)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: softmax_ce expects (N, K) f32 logits + (N) i64 labels -> (1) f32", i);
+        if ((rc = dev_alloc(p, &op.row_loss, static_cast<size_t>(in.d.n))) != TLXCV_OK) break;
+        if ((rc = dev_alloc(p, &op.ticket, 1)) != TLXCV_OK) break;
+        TLX_CUDA(ctx, cudaMemsetAsync(op.ticket, 0, 256, st));
+        op.impl = kImplSoftmaxCe;
+        set_info(op, "softmax_ce", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_MAXPOOL:
         if (d.r != d.s) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: non-square pooling window", i);

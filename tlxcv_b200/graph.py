@@ -141,6 +141,13 @@ class Graph:
             raise ValueError(f"NormalizeToTensor: {c} channels vs {len(layer.mean)} mean/std entries (at most 4)")
         return self._emit("normalize_u8", [x], (n, c, h, w), {}, layer)
 
+    def resize_u8(self, x, size) -> SymTensor:
+        """uint8 (N, Hs, Ws, C) image batch -> uint8 (N, H, W, C), OpenCV INTER_LINEAR (the reference's ``Resize``)."""
+        if x.dtype != "u8" or len(x.shape) != 4:
+            raise TypeError(f"Resize {'.'.join(self._path)}: expects the uint8 (N, H, W, C) image batch")
+        n, _, _, c = x.shape
+        return self._emit("resize_u8", [x], (n, int(size[0]), int(size[1]), c), {}, dtype="u8")
+
     def bn(self, x, layer) -> SymTensor:
         if x.shape[1] != layer.gamma.shape[0]:
             raise ValueError(f"BatchNorm {'.'.join(self._path)}: {x.shape[1]} channels vs {layer.gamma.shape[0]} features")
@@ -222,6 +229,19 @@ class Graph:
         if x.shape[1] != fin:
             raise ValueError(f"Linear {'.'.join(self._path)}: input has {x.shape[1]} features, weights expect {fin}")
         return self._emit("linear", [x], (x.shape[0], fout), {}, layer, dtype="f32")
+
+    def softmax(self, x, axis=-1) -> SymTensor:
+        if len(x.shape) != 2 or axis not in (-1, 1) or x.dtype != "f32":
+            raise NotImplementedError("softmax: only over the class axis of (N, classes) fp32 logits")
+        return self._emit("softmax", [x], x.shape, {}, dtype="f32")
+
+    def softmax_ce(self, logits, target) -> SymTensor:
+        """Mean softmax cross-entropy of (N, classes) logits against (N,) int64 labels -> scalar."""
+        if len(logits.shape) != 2 or logits.dtype != "f32":
+            raise NotImplementedError("softmax_cross_entropy_with_logits: (N, classes) fp32 logits")
+        if target.dtype != "i64" or tuple(target.shape) != (logits.shape[0],):
+            raise NotImplementedError("softmax_cross_entropy_with_logits: target must be (N,) int64 class labels")
+        return self._emit("softmax_ce", [logits, target], (), {}, dtype="f32")
 
     def argmax(self, x, axis=-1) -> SymTensor:
         if len(x.shape) != 2 or axis not in (-1, 1):

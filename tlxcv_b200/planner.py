@@ -23,7 +23,7 @@ from . import graph as _g
 
 # op kinds / activations / dtypes: keep in sync with include/tlxcv_b200.h
 (OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW, OP_IMPORT_U8,
- OP_UPSAMPLE_CONCAT) = range(10)
+ OP_UPSAMPLE_CONCAT, OP_SOFTMAX, OP_SOFTMAX_CE) = range(12)
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY = range(4)
 DT_U8 = 4
 DT_F32, DT_BF16, DT_I64, DT_ACT = 0, 1, 2, 3          # DT_ACT: bf16 in the default mode, f32 in validation mode
@@ -31,7 +31,7 @@ ROLE_INTERNAL, ROLE_INPUT, ROLE_OUTPUT = 0, 1, 2
 
 _ACT = {None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6, "leaky": ACT_LEAKY}
 OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw", "import_u8_nhwc",
-            "upsample_concat"]
+            "upsample_concat", "softmax", "softmax_ce"]
 
 
 @dataclass
@@ -116,6 +116,8 @@ def lower(graph: _g.Graph) -> PlanSpec:
             (n, c), h, w = shape, 1, 1
         elif len(shape) == 1:
             n, c, h, w = shape[0], 1, 1, 1
+        elif len(shape) == 0:
+            n, c, h, w = 1, 1, 1, 1
         else:
             raise NotImplementedError(f"rank-{len(shape)} tensor on the plan")
         spec.tensors.append(TensorSpec(n, h, w, c, dtype, role))
@@ -131,6 +133,15 @@ def lower(graph: _g.Graph) -> PlanSpec:
     # graph inputs: external NCHW fp32 -> internal NHWC (import op)
     for tid in graph.inputs:
         shape = graph.shapes[tid]
+        if graph.dtypes[tid] in ("f32", "i64"):
+            # (N, classes) fp32 logits or (N,) int64 labels handed to a loss / softmax head: used where they lie
+            if (graph.dtypes[tid], len(shape)) not in (("f32", 2), ("i64", 1)):
+                raise NotImplementedError(f"plan input {shape} {graph.dtypes[tid]}: only (N, K) fp32 and (N,) int64 besides images")
+            ext = new_tensor(shape, DT_F32 if graph.dtypes[tid] == "f32" else DT_I64, ROLE_INPUT)
+            spec.inputs.append(ext)
+            gid2plan[tid] = ext
+            produced_at[tid] = -1
+            continue
         if len(shape) != 4:
             raise NotImplementedError(f"plan input must be (N, C, H, W), got {shape}")
         if graph.dtypes[tid] == "u8":
@@ -185,6 +196,15 @@ def lower(graph: _g.Graph) -> PlanSpec:
             spec.ops.append(op)
             gid2plan[cur] = op.out
             produced_at[cur] = i
+            continue
+        if nd.op == "resize_u8":
+            # only as the front of Resize -> Normalize -> ToTensor: the resize runs inside the import pass of the next node
+            j = sole_consumer(nd.out, "normalize_u8")
+            if j is None or spec.tensors[ins[0]].role != ROLE_INPUT:
+                raise NotImplementedError(f"{nd.path}: Resize is supported on the uint8 input batch, directly in front of "
+                                          "NormalizeToTensor")
+            gid2plan[nd.out] = ins[0]
+            produced_at[nd.out] = i
             continue
         if nd.op == "normalize_u8":
             src = spec.tensors[ins[0]]
@@ -271,6 +291,12 @@ def lower(graph: _g.Graph) -> PlanSpec:
         elif nd.op == "argmax":
             out = new_tensor(graph.shapes[nd.out], DT_I64)
             spec.ops.append(OpSpec(OP_ARGMAX, ins[0], out, path=nd.path))
+        elif nd.op == "softmax":
+            out = new_tensor(graph.shapes[nd.out], DT_F32)
+            spec.ops.append(OpSpec(OP_SOFTMAX, ins[0], out, path=nd.path))
+        elif nd.op == "softmax_ce":
+            out = new_tensor(graph.shapes[nd.out], DT_F32)
+            spec.ops.append(OpSpec(OP_SOFTMAX_CE, ins[0], out, in1=ins[1], path=nd.path))
         else:
             raise NotImplementedError(nd.op)
         gid2plan[nd.out] = out
@@ -281,9 +307,9 @@ def lower(graph: _g.Graph) -> PlanSpec:
         pt = gid2plan[tid]
         t = spec.tensors[pt]
         shape = graph.shapes[tid]
+        if t.role == ROLE_INPUT:
+            raise NotImplementedError("a plan input returned unchanged")
         if t.dtype == DT_ACT:
-            if t.role != ROLE_INTERNAL:
-                raise NotImplementedError("a plan input returned unchanged")
             ext = new_tensor((t.n, t.c, t.h, t.w), DT_F32, ROLE_OUTPUT)
             spec.ops.append(OpSpec(OP_EXPORT_NCHW, pt, ext, path="<output>"))
             pt = ext
@@ -322,8 +348,15 @@ def trace(module, args, kwargs, is_tensor, shape_of):
         def to_sym(v):
             if is_tensor(v):
                 flat_inputs.append(v)
-                is_u8 = str(getattr(v, "dtype", "")) == "torch.uint8" or getattr(v, "u8", False)
-                return g.add_input(shape_of(v), "u8" if is_u8 else "act")
+                dt = str(getattr(v, "dtype", getattr(v, "kind", "")))
+                shape = shape_of(v)
+                if dt == "torch.uint8" or getattr(v, "u8", False):
+                    return g.add_input(shape, "u8")
+                if dt in ("torch.int64", "i64"):
+                    return g.add_input(shape, "i64")
+                if len(shape) == 2:
+                    return g.add_input(shape, "f32")
+                return g.add_input(shape, "act")
             return v
 
         s_args = _map_structure(list(args), to_sym)
@@ -356,9 +389,10 @@ def fill_structure(structure, outputs):
 class Shape:
     """Stand-in for a real input tensor when planning on the CPU."""
 
-    def __init__(self, *dims, u8=False):
+    def __init__(self, *dims, u8=False, kind=""):
         self.dims = tuple(int(d) for d in dims)
         self.u8 = bool(u8)      # a uint8 (N, H, W, C) image batch (vision.NormalizeToTensor input)
+        self.kind = kind        # "i64": (N,) int64 class labels
 
 
 def plan_for_shapes(module, *args, **kwargs):

@@ -178,6 +178,8 @@ class Plan:
             raise B200RuntimeError(f"tlxcv_plan_build failed ({rc}): {self.ctx.error()}")
         self.handle = h
         self.n_in, self.n_out = len(spec.inputs), len(spec.outputs)
+        # the C ABI takes output pointers in tensor-table order; the caller's outputs are in forward-return order
+        self._out_order = sorted(range(self.n_out), key=lambda i: spec.outputs[i])
         self.fingerprint = param_fingerprint(spec)
         self._keep = None      # the plan owns packed copies; the fp32 parameters are not referenced after build
 
@@ -198,6 +200,14 @@ class Plan:
             raise ValueError(f"plan takes {self.n_in} inputs")
         for x, ti in zip(inputs, self.spec.inputs):
             t = self.spec.tensors[ti]
+            if t.role == planner.ROLE_INPUT and t.dtype in (planner.DT_F32, planner.DT_I64) and t.h == 1 and t.w == 1 and \
+                    (t.dtype == planner.DT_I64 or x.dim() == 2):
+                want = (t.n,) if t.dtype == planner.DT_I64 else (t.n, t.c)
+                dt = torch.int64 if t.dtype == planner.DT_I64 else torch.float32
+                if tuple(x.shape) != want or x.dtype != dt or not x.is_contiguous() or x.device != self.device:
+                    raise B200RuntimeError(f"plan input must be contiguous {dt} {want} on {self.device}, got {x.dtype} "
+                                           f"{tuple(x.shape)} on {x.device}")
+                continue
             if t.dtype == planner.DT_U8:
                 if tuple(x.shape) != (t.n, t.h, t.w, t.c) or x.dtype != torch.uint8 or not x.is_contiguous() \
                         or x.device != self.device:
@@ -210,7 +220,7 @@ class Plan:
                                        f"{self.device}, got {x.dtype} {tuple(x.shape)} on {x.device}")
         outs = outputs if outputs is not None else self.alloc_outputs()
         ins = (C.c_void_p * self.n_in)(*[x.data_ptr() for x in inputs])
-        ous = (C.c_void_p * self.n_out)(*[o.data_ptr() for o in outs])
+        ous = (C.c_void_p * self.n_out)(*[outs[i].data_ptr() for i in self._out_order])
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.ctx.lib.tlxcv_plan_run(self.handle, ins, ous, C.c_void_p(stream), 1 if graph else 0)
         if rc != 0:
@@ -223,7 +233,7 @@ class Plan:
             if t.device.type != "cpu" or not t.is_pinned() or not t.is_contiguous():
                 raise B200RuntimeError("run_host needs contiguous pinned host tensors")
         ins = (C.c_void_p * self.n_in)(*[x.data_ptr() for x in host_inputs])
-        ous = (C.c_void_p * self.n_out)(*[o.data_ptr() for o in host_outputs])
+        ous = (C.c_void_p * self.n_out)(*[host_outputs[i].data_ptr() for i in self._out_order])
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.ctx.lib.tlxcv_plan_run_host(self.handle, ins, ous, C.c_void_p(stream), 1 if graph else 0)
         if rc != 0:
@@ -235,7 +245,7 @@ class Plan:
         n = self.ctx.lib.tlxcv_plan_num_ops(self.handle)
         ms = (C.c_float * n)()
         ins = (C.c_void_p * self.n_in)(*[x.data_ptr() for x in inputs])
-        ous = (C.c_void_p * self.n_out)(*[o.data_ptr() for o in outs])
+        ous = (C.c_void_p * self.n_out)(*[outs[i].data_ptr() for i in self._out_order])
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self.ctx.lib.tlxcv_plan_profile(self.handle, ins, ous, C.c_void_p(stream), ms, n)
         if rc != 0:
@@ -320,7 +330,7 @@ def get_plan(module, args, kwargs, precision=None):
 
 def run_module(module, args, kwargs):
     plan, structure, flat_inputs = get_plan(module, args, kwargs)
-    ins = [x if (x.dtype in (torch.float32, torch.uint8) and x.is_contiguous()) else
-           (x.contiguous() if x.dtype == torch.uint8 else x.float().contiguous()) for x in flat_inputs]
+    ins = [x if (x.dtype in (torch.float32, torch.uint8, torch.int64) and x.is_contiguous()) else
+           (x.contiguous() if x.dtype in (torch.uint8, torch.int64) else x.float().contiguous()) for x in flat_inputs]
     outs = plan.run(ins)
     return planner.fill_structure(structure, outs)

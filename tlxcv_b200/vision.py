@@ -42,13 +42,36 @@ class NormalizeToTensor(nn.Module):
         return g.normalize_u8(x, self)
 
 
-class Preprocessed(nn.Module):
-    """``backbone(NormalizeToTensor(mean, std)(images_uint8_nhwc))`` as one module / one plan."""
+class Resize(nn.Module):
+    """``Resize((H, W))`` of the reference's transform pipeline (demo/image_classification/predict-resnet.py:51) for a uint8
+    NHWC batch: bilinear, bit-identical to ``cv2.resize(img, (W, H), interpolation=cv2.INTER_LINEAR)`` - what tensorlayerx's
+    ``Resize`` runs on a numpy image (oracle/cv_resize.py restates it).  Executes inside the input pass of the
+    ``NormalizeToTensor`` that must follow it: the resized uint8 image never exists in memory."""
 
-    def __init__(self, backbone, mean, std, name=None):
+    def __init__(self, size, interpolation="bilinear", name=None):
         super().__init__(name=name)
+        if interpolation != "bilinear":
+            raise NotImplementedError("Resize: only bilinear interpolation is on the B200 path")
+        self.size = (int(size), int(size)) if isinstance(size, int) else (int(size[0]), int(size[1]))
+
+    def forward(self, x):
+        g = _g.active()
+        if g is None or not isinstance(x, _g.SymTensor):
+            raise RuntimeError("Resize only executes inside a traced plan (call the enclosing module with a uint8 (N, H, W, C) "
+                               "CUDA tensor)")
+        return g.resize_u8(x, self.size)
+
+
+class Preprocessed(nn.Module):
+    """``backbone(NormalizeToTensor(mean, std)([Resize(size)](images_uint8_nhwc)))`` as one module / one plan."""
+
+    def __init__(self, backbone, mean, std, resize=None, name=None):
+        super().__init__(name=name)
+        self.resize = Resize(resize) if resize is not None else None
         self.preprocess = NormalizeToTensor(mean, std)
         self.backbone = backbone
 
     def forward(self, images):
+        if self.resize is not None:
+            images = self.resize(images)
         return self.backbone(self.preprocess(images))
