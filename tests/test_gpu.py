@@ -839,3 +839,76 @@ def test_resize_normalize_totensor_fused_into_the_input_kernel(hs, ws, size):
     plan = next(iter(net.__dict__["_b200_plans"].values()))[0]
     k0 = plan.op_info(0)["kernel"]
     assert k0.startswith("import_u8_resize") if (hs, ws) != (size, size) else k0.startswith("import_u8_nhwc"), k0
+
+
+@pytest.mark.parametrize("cin,mid,cout,hw,stride,n,res", [(64, 64, 256, 14, 1, 3, True), (128, 128, 512, 12, 1, 2, True),
+                                                           (256, 128, 512, 15, 2, 2, False), (72, 64, 136, 9, 1, 5, True),
+                                                           (64, 64, 256, 56, 1, 4, True), (128, 128, 512, 28, 1, 9, True)])
+def test_conv_to_1x1_chain_kernel(cin, mid, cout, hw, stride, n, res):
+    """relu(bn3(conv3(relu(bn2(conv2(h))))) + x) of a bottleneck (resnet.py:146-155) as ONE chain kernel: the 64 / 128-channel
+    map between the 3x3 and the 1x1 stays in shared memory.  Must agree with the two-kernel pipeline (TLXCV_NO_CHAIN) to the
+    last bf16 rounding and with fp32 math on bf16-rounded operands."""
+    from tlxcv_b200 import nn, runtime
+
+    g = torch.Generator().manual_seed(cin + hw + cout)
+    x = torch.randn(n, cin, hw, hw, generator=g)
+    po = (hw + 2 - 3) // stride + 1
+    r = torch.randn(n, cout, po, po, generator=g) if res else None
+
+    def bn_params(c):
+        return dict(beta=torch.randn(c, generator=g) * 0.1, gamma=0.75 + 0.5 * torch.rand(c, generator=g),
+                    moving_mean=torch.randn(c, generator=g) * 0.1, moving_var=0.75 + 0.5 * torch.rand(c, generator=g))
+
+    w2 = torch.randn(mid, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5
+    w3 = torch.randn(cout, mid, 1, 1, generator=g) * (1.0 / mid) ** 0.5
+    b2, b3 = bn_params(mid), bn_params(cout)
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv2 = nn.GroupConv2d(in_channels=cin, out_channels=mid, kernel_size=3, stride=stride, padding=1, b_init=None)
+            self.bn2 = nn.BatchNorm2d(num_features=mid)
+            self.conv3 = nn.GroupConv2d(in_channels=mid, out_channels=cout, kernel_size=1, stride=1, padding=0, b_init=None)
+            self.bn3 = nn.BatchNorm2d(num_features=cout)
+            self.relu = nn.ReLU()
+
+        def forward(self, x, r=None):
+            out = self.bn3(self.conv3(self.relu(self.bn2(self.conv2(x)))))
+            if r is not None:
+                out += r
+            return self.relu(out)
+
+    sd = {"conv2.filters": w2, "conv3.filters": w3}
+    for name, b in (("bn2", b2), ("bn3", b3)):
+        sd.update({f"{name}.{k}": v for k, v in b.items()})
+
+    def run():
+        net = Net()
+        net.load_state_dict(sd)
+        net = net.cuda().set_eval()
+        args = (x.cuda(),) if r is None else (x.cuda(), r.cuda())
+        plan, _, flat = runtime.get_plan(net, args, {})
+        a = plan.run(flat, graph=False)[0].cpu()
+        b = plan.run(flat, graph=True)[0].cpu()
+        assert torch.equal(a, b)
+        return a, [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))], plan.num_launches
+
+    fused, kernels, launches = run()
+    assert any(k.startswith("conv_chain_3x3") for k in kernels), kernels
+    os.environ["TLXCV_NO_CHAIN"] = "1"
+    try:
+        unfused, kernels2, launches2 = run()
+    finally:
+        del os.environ["TLXCV_NO_CHAIN"]
+    assert not any(k.startswith("conv_chain") for k in kernels2) and launches2 == launches + 1
+    q = lambda t: t.bfloat16().float()
+    bn = lambda t, b: F.batch_norm(t, b["moving_mean"], b["moving_var"], b["gamma"], b["beta"], False, 0.0, 1e-5)
+    h = q(F.relu(bn(F.conv2d(q(x), q(w2), None, stride, 1), b2)))
+    y = bn(F.conv2d(h, q(w3)), b3)
+    y = F.relu(y + q(r)) if res else F.relu(y)
+    tol = 2.0 ** -7 * max(1.0, float(y.abs().max()))
+    assert fused.shape == y.shape
+    assert float((fused - y).abs().max()) <= tol
+    assert float((unfused - y).abs().max()) <= tol
+    # same operands, same bf16 intermediate, fp32 accumulation in another order: within one bf16 ulp of each other
+    assert float((fused - unfused).abs().max()) <= 2.0 ** -7 * max(1.0, float(y.abs().max()))

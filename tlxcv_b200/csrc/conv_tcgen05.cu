@@ -207,6 +207,13 @@ struct EpiArgs {
   float alpha1, alpha2;
   int ablate;
   unsigned long long* trace;
+  // CHAIN kernels (conv -> 1x1 conv in one launch, see conv_chain_kernel): the warp walks whole M tiles (all N chunks of
+  // one M tile, then the M tile n_workers further on) and, at the first chunk of every M tile, first turns the finished
+  // first-GEMM accumulator into the bf16 A operand of the second GEMM
+  int chain_m_tiles;                                      // M tiles of the layer
+  uint32_t acc1_full_bar, acc1_empty_bar, a2_full_bar, a2_empty_bar;  // shared-space addresses ([2], [2], [1], [1])
+  uint32_t a2_smem;                                       // A2 operand: N1 / 64 SWIZZLE_128B K blocks of 128 rows x 128 B
+  const float* sc1_cache;                                 // smem [scale1(N1) | shift1(N1)]
 };
 
 template <int ACT>
@@ -227,9 +234,16 @@ __device__ __forceinline__ float act1f(float v, float alpha) {
 // DUAL: the tile has TWO accumulators (conv3 of a bottleneck and the block's downsample conv, see the kernel):
 //     y = act1( acc1 * scale + shift  +  acc2 * scale2 + shift2 )
 // the scale/shift buffer then holds [scale | scale2 | shift + shift2] for the tile's BLOCK_N = 128 channels.
-template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool DUAL = false>
+// CHAIN_N1 > 0: second half of a chain kernel (BLOCK_N = 128 chunks of the 1x1 conv), with the first-GEMM hand-over (chain_e1)
+// at the start of every M tile; the first GEMM is N1 channels wide.
+template <int N1>
+__device__ __forceinline__ void chain_e1(const EpiArgs& a, int lg, int cgroup, int lane, uint32_t tile_i);
+
+template <int BLOCK_N, int ACT1, bool RES, int ACT2, bool F32, int kRing, bool DUAL = false, int CHAIN_N1 = 0>
 __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgroup, int lane) {
   static_assert(!DUAL || (BLOCK_N == 128 && !RES && !F32), "dual accumulators: 128-wide bf16 tiles without a residual");
+  static_assert(CHAIN_N1 == 0 || (BLOCK_N == 128 && !DUAL && !F32), "chain kernels: 128-wide bf16 chunks");
+  constexpr bool CHAIN = CHAIN_N1 > 0;
   constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
   // chunks per warp per tile: the tile's BLOCK_N / 32 chunks over epi_warps / 4 column groups (compile-time for the
   // 8-warp build; a.cpw when kEpiWarps is raised for experiments)
@@ -241,9 +255,14 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   // prefetch cursor (only lane 0 advances it): walks the same item sequence, two items ahead (one for a 2-slot ring)
   // (m_pair, n_tile) of a tile index advance incrementally by (dm, dn) per tile_stride: an integer division per tile
   // costs this warp ~200 dependent cycles, three of them were 8 % of a short-K tile
-  const int dm = a.tile_stride / a.n_tiles, dn = a.tile_stride - dm * a.n_tiles;
-  const int first_m = a.first_tile / a.n_tiles, first_n = a.first_tile - first_m * a.n_tiles;
-  int pf_tile = a.first_tile, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0, pf_mp = first_m, pf_nt = first_n;
+  // a plain kernel's units are the tiles first_tile, first_tile + tile_stride, ... < num_tiles; a chain kernel's units
+  // are the n_tiles chunks of M tile first_tile, then those of M tile first_tile + tile_stride, ...
+  const int dm = CHAIN ? 0 : a.tile_stride / a.n_tiles, dn = CHAIN ? 1 : a.tile_stride - dm * a.n_tiles;
+  const int carry = CHAIN ? a.tile_stride : 1;
+  const int first_m = CHAIN ? a.first_tile : a.first_tile / a.n_tiles, first_n = CHAIN ? 0 : a.first_tile - first_m * a.n_tiles;
+  const int n_units = CHAIN ? (a.first_tile < a.chain_m_tiles ? ((a.chain_m_tiles - 1 - a.first_tile) / a.tile_stride + 1) * a.n_tiles : 0)
+                            : (a.first_tile < a.num_tiles ? (a.num_tiles - 1 - a.first_tile) / a.tile_stride + 1 : 0);
+  int pf_u = 0, pf_ci = 0, pf_m0 = 0, pf_n0 = 0, pf_nmy = 0, pf_mp = first_m, pf_nt = first_n;
   uint32_t pf = 0;
   auto pf_place = [&]() {
     const int m_pair = pf_mp, n_tile = pf_nt;
@@ -253,14 +272,14 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     pf_nmy = min(min(kCpw, BLOCK_N / 32 - c_first), max(0, (a.Cout - (pf_n0 + c_first * 32) + 31) / 32));
   };
   auto pf_issue = [&]() {  // issue the residual load of the next valid item, if any
-    while (pf_tile < a.num_tiles && pf_ci >= pf_nmy) {
+    while (pf_u < n_units && pf_ci >= pf_nmy) {
       pf_ci = 0;
-      pf_tile += a.tile_stride;
+      ++pf_u;
       pf_mp += dm, pf_nt += dn;
-      if (pf_nt >= a.n_tiles) pf_nt -= a.n_tiles, ++pf_mp;
-      if (pf_tile < a.num_tiles) pf_place();
+      if (pf_nt >= a.n_tiles) pf_nt -= a.n_tiles, pf_mp += carry;
+      if (pf_u < n_units) pf_place();
     }
-    if (pf_tile >= a.num_tiles || (a.ablate & 16)) return;
+    if (pf_u >= n_units || (a.ablate & 16)) return;
     const uint32_t slot = pf & (kRing - 1);
     const uint32_t bar = a.res_bar + slot * 8;
     mbar_arrive_expect_tx(bar, 2048);
@@ -269,7 +288,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     ++pf_ci;
   };
   if (RES && lane == 0) {
-    if (pf_tile < a.num_tiles) pf_place();
+    if (pf_u < n_units) pf_place();
 #pragma unroll
     for (int k = 0; k < (kRing == 4 ? 2 : 1); ++k) pf_issue();
   }
@@ -297,11 +316,15 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       sh2_nx = __ldg(reinterpret_cast<const float4*>(a.shift2 + nn0) + lane);
     }
   };
-  if (sc_lane && a.first_tile < a.num_tiles) fetch_sc(first_n);
-  int m_pair = first_m - dm, n_tile = first_n - dn;  // advanced at the top of every iteration
-  for (int tile = a.first_tile; tile < a.num_tiles; tile += a.tile_stride) {
-    m_pair += dm, n_tile += dn;
-    if (n_tile >= a.n_tiles) n_tile -= a.n_tiles, ++m_pair;
+  if (sc_lane && n_units > 0) fetch_sc(first_n);
+  int m_pair = first_m, n_tile = first_n;
+  uint32_t chain_i = 0;  // CHAIN: M tiles started by this CTA
+  for (int unit = 0; unit < n_units; ++unit) {
+    if (unit > 0) {
+      m_pair += dm, n_tile += dn;
+      if (n_tile >= a.n_tiles) n_tile -= a.n_tiles, m_pair += carry;
+    }
+    if (CHAIN && n_tile == 0) chain_e1<CHAIN_N1 == 0 ? 64 : CHAIN_N1>(a, lg, cgroup, lane, chain_i++);
     const int m_tile = a.two ? 2 * m_pair + a.rank : m_pair;
     const int m0 = m_tile * kBlockM + lg * 32, n0 = n_tile * BLOCK_N;
     const int n_my = max(0, min(min(kCpw, BLOCK_N / 32 - c_first), (a.Cout - (n0 + c_first * 32) + 31) / 32));  // chunks with real channels
@@ -310,7 +333,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     // this warp's slice of the tile's scale / shift was requested one tile ago (an epilogue-bound layer finds its
     // accumulator already complete, so a load issued here would be fully exposed); request the next tile's now
     const float4 sc_pf = sc_nx, sh_pf = sh_nx, sc2_pf = sc2_nx, sh2_pf = sh2_nx;
-    if (sc_lane && tile + a.tile_stride < a.num_tiles) fetch_sc(n_tile + dn >= a.n_tiles ? n_tile + dn - a.n_tiles : n_tile + dn);
+    if (sc_lane && unit + 1 < n_units) fetch_sc(n_tile + dn >= a.n_tiles ? n_tile + dn - a.n_tiles : n_tile + dn);
     if (btracer) trace_c(a.trace, 2, tr);  // [5k+1] tile set-up done
     mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
     tcgen05_fence_after();
@@ -948,6 +971,345 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// CHAIN: conv (3x3 / strided / any im2col geometry, N1 = 64 or 128 output channels) + BN + ReLU  ->  1x1 conv + BN
+// (+ residual) (+ ReLU) in ONE launch: the tail of a ResNet bottleneck, `relu(bn3(conv3(relu(bn2(conv2(h))))) + x)`
+// (classification/resnet.py:146-155), without the N1-channel intermediate ever reaching HBM, and with the MMA-bound
+// 3x3 running under the HBM-bound 1x1's output traffic.
+//   GEMM1  acc1[128 px][N1]   = im2col(h)[128][K1] * W1[N1][K1]^T     (TMEM columns 256.., double buffered)
+//   E1     A2 = bf16(relu(acc1 * scale1 + shift1))  written by the epilogue warps straight into shared memory in the
+//          SWIZZLE_128B K-major layout tcgen05.mma reads (N1 / 64 K blocks of 128 rows x 128 B)
+//   GEMM2  acc2[128 px][128]  = A2[128][N1] * W2[chunk][N1]^T         per 128-channel chunk of the 1x1 conv (TMEM columns
+//          0..255, double buffered), W2 chunks streamed through the operand ring
+//   E2     the ordinary epilogue (scale / shift, residual by TMA, ReLU, TMA store) per chunk
+// One operand ring serves both GEMMs; producer and MMA warp walk the same static item order per CTA: the K blocks of G1(i)
+// with the chunks of G2(i-1) slotted in at even spacing, then G2(last) - the tensor pipe works on G1(i) while the epilogue
+// warps drain the chunks of tile i-1, and turns acc1(i) into A2 while G1(i+1) has already begun.
+// (Measured on the first version, which issued all of G2(i-1) after G1(i): the epilogue warps idled for the whole first GEMM.)
+// ------------------------------------------------------------------------------------------------
+constexpr int kChainBarBase = 2 * kMaxStages + 8 + kEpiWarps * kMaxRing;  // after the residual barriers (index 56)
+
+template <int N1>
+__device__ __forceinline__ void chain_e1(const EpiArgs& a, int lg, int cgroup, int lane, uint32_t tile_i) {
+  constexpr int kChunks = N1 / 32;            // 32-channel chunks of acc1
+  constexpr int kCpw1 = kChunks / 2;          // per warp (two column groups)
+  const uint32_t b = tile_i & 1u;
+  mbar_wait(a.acc1_full_bar + b * 8, (tile_i >> 1) & 1u);
+  tcgen05_fence_after();
+  // the second GEMM of the previous tile has finished reading A2 (first tile: passes at once)
+  mbar_wait(a.a2_empty_bar, (tile_i & 1u) ^ 1u);
+  const int row = lg * 32 + lane;
+  const uint32_t row_base = a.a2_smem + static_cast<uint32_t>(row) * 128u;
+  const uint32_t swz = static_cast<uint32_t>(row & 7);
+#pragma unroll
+  for (int ci = 0; ci < kCpw1; ++ci) {
+    const int chunk = cgroup * kCpw1 + ci;
+    uint32_t v[32];
+    tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + 256u + b * N1 + chunk * 32, v);
+    tmem_ld_wait();
+    const ulonglong2* scp = reinterpret_cast<const ulonglong2*>(a.sc1_cache + chunk * 32);
+    const ulonglong2* shp = reinterpret_cast<const ulonglong2*>(a.sc1_cache + N1 + chunk * 32);
+    const uint32_t kb_base = row_base + static_cast<uint32_t>((chunk * 32) / 64) * kABytes;
+    const uint32_t j0 = static_cast<uint32_t>(((chunk * 32) % 64) / 8);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 8 channels = one 16-byte piece of the row
+      const ulonglong2 sc0 = scp[2 * q], sc1 = scp[2 * q + 1], sh0 = shp[2 * q], sh1 = shp[2 * q + 1];
+      const uint32_t o0 = pack_pair_bf16_act<TLXCV_ACT_RELU>(ffma2(pack_u64(v[8 * q], v[8 * q + 1]), sc0.x, sh0.x));
+      const uint32_t o1 = pack_pair_bf16_act<TLXCV_ACT_RELU>(ffma2(pack_u64(v[8 * q + 2], v[8 * q + 3]), sc0.y, sh0.y));
+      const uint32_t o2 = pack_pair_bf16_act<TLXCV_ACT_RELU>(ffma2(pack_u64(v[8 * q + 4], v[8 * q + 5]), sc1.x, sh1.x));
+      const uint32_t o3 = pack_pair_bf16_act<TLXCV_ACT_RELU>(ffma2(pack_u64(v[8 * q + 6], v[8 * q + 7]), sc1.y, sh1.y));
+      asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(kb_base + (((j0 + q) ^ swz) << 4)), "r"(o0), "r"(o1), "r"(o2), "r"(o3)
+                   : "memory");
+    }
+  }
+  fence_proxy_async_smem();  // generic-proxy stores -> visible to the tensor core's (async proxy) operand reads
+  tcgen05_fence_before();
+  __syncwarp();
+  if (lane == 0) {
+    mbar_arrive(a.acc1_empty_bar + b * 8);  // acc1[b] may be overwritten by the first GEMM of tile i + 2
+    mbar_arrive(a.a2_full_bar);             // one arrival per epilogue warp: A2 complete when all eight are in
+  }
+}
+
+// W1RES: the first conv's weights (num_kb1 K blocks of N1 x 64) stay RESIDENT in shared memory for the whole launch instead
+// of being streamed again for every tile: the chain kernels are bound by the bytes an SM can take in (~45 B/clk measured,
+// tools/micro/l2_feed.cu - the same for data every SM reads and for data only one reads, multicast does not help), and for
+// the 64 -> 64 3x3 the weights are 72 KB of the 376 KB a tile pulls in.
+template <int N1, bool W1RES>
+struct ChainCfg {
+  static constexpr int kB1Bytes = N1 * 128;                  // one K block of W1
+  static constexpr int kSlot = W1RES ? kABytes : kABytes + kB1Bytes;  // A tile [| W1 K block]; a W2 item uses the A part
+  static constexpr int kA2Bytes = (N1 / 64) * kABytes;
+  static constexpr int kSc1Bytes = 1024;                     // [scale1 | shift1], N1 <= 128 floats each
+  static constexpr int fixed_bytes(int ring, int num_kb1) {
+    return (W1RES ? num_kb1 * kB1Bytes : 0) + kA2Bytes + kEpiWarps * ring * 2048 + 2 * kScaleBufBytes + kSc1Bytes + kBarrierBytes;
+  }
+  static constexpr int stages_for(int ring, int num_kb1) {
+    const int n = (kSmemLimit - fixed_bytes(ring, num_kb1)) / kSlot;
+    return n > kMaxStages ? kMaxStages : n;
+  }
+  static constexpr int smem_bytes(int ring, int num_kb1) { return stages_for(ring, num_kb1) * kSlot + fixed_bytes(ring, num_kb1); }
+};
+
+template <int N1, bool W1RES>
+__global__ void __launch_bounds__(kThreadsBase, 1)
+conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
+                  const __grid_constant__ CUtensorMap tmapB2, const __grid_constant__ CUtensorMap tmapOut,
+                  const __grid_constant__ CUtensorMap tmapRes, const ConvKernelParams p) {
+  using CC = ChainCfg<N1, W1RES>;
+  constexpr int BLOCK_N = 128;      // chunk width of the second GEMM
+  constexpr int kKb2 = N1 / 64;     // K blocks of the second GEMM
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  if ((smem_u32(smem_raw) & 1023u) != 0) __trap();
+  const int n_stages = p.stages, ring = p.ring;
+  uint8_t* w1res = smem_raw;                                              // W1RES: num_kb1 K blocks of W1
+  uint8_t* smem = smem_raw + (W1RES ? p.num_kb1 * CC::kB1Bytes : 0);      // operand ring
+  uint8_t* a2 = smem + n_stages * CC::kSlot;
+  uint8_t* staging = a2 + CC::kA2Bytes;
+  const int staging_bytes = kEpiWarps * ring * 2048;
+  float* sc_cache = reinterpret_cast<float*>(staging + staging_bytes);
+  float* sc1_cache = reinterpret_cast<float*>(staging + staging_bytes + 2 * kScaleBufBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + 2 * kScaleBufBytes + CC::kSc1Bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + kMaxStages;
+  uint64_t* tmem_full_bar = bars + 2 * kMaxStages;   // acc2
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  uint64_t* res_bar = bars + 2 * kMaxStages + 8;
+  uint64_t* acc1_full_bar = bars + kChainBarBase;    // [2]
+  uint64_t* acc1_empty_bar = acc1_full_bar + 2;      // [2]
+  uint64_t* a2_full_bar = acc1_empty_bar + 2;        // [1]
+  uint64_t* a2_empty_bar = a2_full_bar + 1;          // [1]
+  uint64_t* w1_full_bar = a2_empty_bar + 1;          // [1]  W1RES: resident weights landed
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int worker = blockIdx.x, n_workers = gridDim.x;
+  const int m_tiles = p.m_tiles, n_chunks = p.n_tiles;
+  const int my_tiles = worker < m_tiles ? (m_tiles - 1 - worker) / n_workers + 1 : 0;
+
+  if (warp == 1 && lane == 0) {
+    tma_prefetch_desc(&tmapA);
+    tma_prefetch_desc(&tmapB);
+    tma_prefetch_desc(&tmapB2);
+    tma_prefetch_desc(&tmapOut);
+    for (int i = 0; i < n_stages; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tmem_full_bar[i]), 1);
+      mbar_init(smem_u32(&tmem_empty_bar[i]), kEpiWarps);
+      mbar_init(smem_u32(&acc1_full_bar[i]), 1);
+      mbar_init(smem_u32(&acc1_empty_bar[i]), kEpiWarps);
+    }
+    mbar_init(smem_u32(a2_full_bar), kEpiWarps);
+    mbar_init(smem_u32(a2_empty_bar), 1);
+    mbar_init(smem_u32(w1_full_bar), 1);
+    for (int i = 0; i < kEpiWarps * kMaxRing; ++i) mbar_init(smem_u32(&res_bar[i]), 1);
+    if (p.residual != nullptr) tma_prefetch_desc(&tmapRes);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<512>(smem_u32(tmem_ptr_smem));
+  const bool sc_cached = n_chunks == 1;
+  if (warp >= 2) {
+    for (int i = threadIdx.x - 64; i < N1; i += kEpiWarps * 32) {  // first BN: N1 scale / shift pairs, constant for the launch
+      sc1_cache[i] = p.scale2[i];
+      sc1_cache[N1 + i] = p.shift2[i];
+    }
+    if (sc_cached)
+      for (int i = threadIdx.x - 64; i < BLOCK_N; i += kEpiWarps * 32) {
+        sc_cache[i] = p.scale[i];
+        sc_cache[256 + i] = p.shift[i];
+      }
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      PipeState ps;
+      const int PQ = p.P * p.Q;
+      // Static item order shared with the MMA warp: the K blocks of G1(i), with the chunks of G2(i - 1) slotted in after K block
+      // (c + 1) * K1 / (n_chunks + 1) - 1, so that the epilogue warps drain tile i - 1 while the tensor pipe works on tile i.
+      auto load_g2_chunk = [&](int c) {
+        for (int kb2 = 0; kb2 < kKb2; ++kb2) {
+          mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[ps.stage]);
+          mbar_arrive_expect_tx(bar, kABytes);
+          tma_load_2d(smem_u32(smem + ps.stage * CC::kSlot), &tmapB2, bar, kb2 * kBlockK, c * BLOCK_N);
+          ps.advance(n_stages);
+        }
+      };
+      if (W1RES && my_tiles > 0) {  // weights are parameters, not activations: they could even precede pdl_wait
+        mbar_arrive_expect_tx(smem_u32(w1_full_bar), p.num_kb1 * CC::kB1Bytes);
+        for (int kb = 0; kb < p.num_kb1; ++kb) tma_load_2d(smem_u32(w1res + kb * CC::kB1Bytes), &tmapB, smem_u32(w1_full_bar), kb * kBlockK, 0);
+      }
+      for (int i = 0; i < my_tiles; ++i) {
+        const int m0 = (worker + i * n_workers) * kBlockM;
+        const int img = m0 / PQ;
+        const int rem = m0 - img * PQ;
+        const int op = rem / p.Q, oq = rem - op * p.Q;
+        const int base_h = op * p.stride - p.pad, base_w = oq * p.stride - p.pad;
+        int r = 0, sx = 0, cb = 0, c_next = 0;
+        for (int kb = 0; kb < p.num_kb1; ++kb) {
+          if (i > 0 && c_next < n_chunks && kb == ((c_next + 1) * p.num_kb1) / (n_chunks + 1)) load_g2_chunk(c_next++);
+          mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+          const uint32_t bar = smem_u32(&full_bar[ps.stage]);
+          const uint32_t dst = smem_u32(smem + ps.stage * CC::kSlot);
+          mbar_arrive_expect_tx(bar, CC::kSlot);  // == kABytes when the weights are resident
+          tma_load_im2col_4d(dst, &tmapA, bar, cb * kBlockK, base_w, base_h, img, static_cast<uint16_t>(sx * p.dil),
+                             static_cast<uint16_t>(r * p.dil));
+          if (++cb == p.kb_per_tap) {
+            cb = 0;
+            if (++sx == p.S) sx = 0, ++r;
+          }
+          if (!W1RES) tma_load_2d(dst + kABytes, &tmapB, bar, kb * kBlockK, 0);
+          ps.advance(n_stages);
+        }
+        if (i > 0)
+          while (c_next < n_chunks) load_g2_chunk(c_next++);
+      }
+      if (my_tiles > 0)
+        for (int c = 0; c < n_chunks; ++c) load_g2_chunk(c);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (converged warp, one elected lane) =====================
+    constexpr uint32_t idesc1 = make_idesc_bf16(kBlockM, N1);
+    constexpr uint32_t idesc2 = make_idesc_bf16(kBlockM, BLOCK_N);
+    constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+    const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t a2_lo = ((smem_u32(a2) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t w1_lo = ((smem_u32(w1res) & 0x3FFFFu) >> 4) | (1u << 16);
+    const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
+    PipeState ps;
+    uint32_t acc2 = 0, acc2_phase = 0;
+    if (W1RES && my_tiles > 0) {
+      mbar_wait(smem_u32(w1_full_bar), 0);
+      tcgen05_fence_after();
+    }
+    auto issue_g2_chunk = [&](uint32_t j, int c) {
+      if (c == 0) {
+        mbar_wait(smem_u32(a2_full_bar), j & 1u);  // the epilogue warps have written A2 of tile j
+        tcgen05_fence_after();
+      }
+      mbar_wait(smem_u32(&tmem_empty_bar[acc2]), acc2_phase ^ 1);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + acc2 * BLOCK_N;
+      for (int kb2 = 0; kb2 < kKb2; ++kb2) {
+        const uint32_t st = ps.stage;
+        mbar_wait(full0 + st * 8, ps.phase);
+        ps.advance(n_stages);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a2_lo + kb2 * (kABytes >> 4);
+          const uint32_t b_lo = smem_lo + st * (CC::kSlot >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_lohi<false>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc2, (kb2 != 0 || k != 0) ? 1u : 0u);
+          umma_commit(empty0 + st * 8);
+          if (kb2 == kKb2 - 1) {
+            umma_commit(smem_u32(&tmem_full_bar[acc2]));
+            if (c == n_chunks - 1) umma_commit(smem_u32(a2_empty_bar));  // every MMA that reads A2 of this tile has retired
+          }
+        }
+        __syncwarp();
+      }
+      if (++acc2 == 2) acc2 = 0, acc2_phase ^= 1;
+    };
+    for (int i = 0; i < my_tiles; ++i) {
+      const uint32_t b = static_cast<uint32_t>(i) & 1u;
+      mbar_wait(smem_u32(&acc1_empty_bar[b]), ((static_cast<uint32_t>(i) >> 1) & 1u) ^ 1u);
+      tcgen05_fence_after();
+      const uint32_t tmem_d = tmem_base + 256u + b * N1;
+      int c_next = 0;
+      for (int kb = 0; kb < p.num_kb1; ++kb) {
+        if (i > 0 && c_next < n_chunks && kb == ((c_next + 1) * p.num_kb1) / (n_chunks + 1)) {
+          issue_g2_chunk(static_cast<uint32_t>(i - 1), c_next);
+          ++c_next;
+        }
+        const uint32_t st = ps.stage;
+        mbar_wait(full0 + st * 8, ps.phase);
+        ps.advance(n_stages);
+        tcgen05_fence_after();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = smem_lo + st * (CC::kSlot >> 4);
+          const uint32_t b_lo = W1RES ? w1_lo + kb * (CC::kB1Bytes >> 4) : a_lo + (kABytes >> 4);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k)
+            umma_bf16_lohi<false>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc1, (kb != 0 || k != 0) ? 1u : 0u);
+          umma_commit(empty0 + st * 8);
+          if (kb == p.num_kb1 - 1) umma_commit(smem_u32(&acc1_full_bar[b]));
+        }
+        __syncwarp();
+      }
+      if (i > 0)
+        for (; c_next < n_chunks; ++c_next) issue_g2_chunk(static_cast<uint32_t>(i - 1), c_next);
+    }
+    if (my_tiles > 0)
+      for (int c = 0; c < n_chunks; ++c) issue_g2_chunk(static_cast<uint32_t>(my_tiles - 1), c);
+  } else {
+    // ===================== epilogue: 8 warps =====================
+    EpiArgs a;
+    a.tmem_base = tmem_base;
+    a.tmem_full_bar = smem_u32(tmem_full_bar);
+    a.tmem_empty_bar = smem_u32(tmem_empty_bar);
+    a.ring = smem_u32(staging + (warp - 2) * (ring * 2048));
+    a.res_bar = smem_u32(res_bar + (warp - 2) * kMaxRing);
+    a.sc_cache = sc_cache;
+    a.sc_mode = sc_cached ? 0 : 1;
+    a.scale2 = nullptr, a.shift2 = nullptr;
+    a.cpw = 2;
+    a.scale = p.scale, a.shift = p.shift;
+    a.out_f32 = nullptr;
+    a.amax_keys = nullptr;
+    a.tmap_out = &tmapOut, a.tmap_res = &tmapRes;
+    a.M = p.M, a.Cout = p.Cout, a.n_tiles = n_chunks, a.num_tiles = m_tiles * n_chunks;
+    a.first_tile = worker, a.tile_stride = n_workers;
+    a.two = 0, a.rank = 0, a.tmem_empty_remote = 0;
+    a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
+    a.ablate = 0;
+    a.trace = nullptr;
+    a.chain_m_tiles = m_tiles;
+    a.acc1_full_bar = smem_u32(acc1_full_bar), a.acc1_empty_bar = smem_u32(acc1_empty_bar);
+    a.a2_full_bar = smem_u32(a2_full_bar), a.a2_empty_bar = smem_u32(a2_empty_bar);
+    a.a2_smem = smem_u32(a2);
+    a.sc1_cache = sc1_cache;
+    const int lg = warp & 3, cgroup = (warp - 2) >> 2;
+    const bool res = p.residual != nullptr;
+    const bool relu2 = p.act2 == TLXCV_ACT_RELU;
+    // y = act2(acc2 * scale + shift + residual) or act1(acc2 * scale + shift); act in {none, relu} (checked by the planner)
+    if (res) {
+      if (relu2) {
+        if (ring == 2) epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, true, TLXCV_ACT_RELU, false, 2, false, N1>(a, lg, cgroup, lane);
+        else epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, true, TLXCV_ACT_RELU, false, 4, false, N1>(a, lg, cgroup, lane);
+      } else {
+        if (ring == 2) epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, true, TLXCV_ACT_NONE, false, 2, false, N1>(a, lg, cgroup, lane);
+        else epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, true, TLXCV_ACT_NONE, false, 4, false, N1>(a, lg, cgroup, lane);
+      }
+    } else if (p.act1 == TLXCV_ACT_RELU) {
+      if (ring == 2) epilogue_loop<BLOCK_N, TLXCV_ACT_RELU, false, TLXCV_ACT_NONE, false, 2, false, N1>(a, lg, cgroup, lane);
+      else epilogue_loop<BLOCK_N, TLXCV_ACT_RELU, false, TLXCV_ACT_NONE, false, 4, false, N1>(a, lg, cgroup, lane);
+    } else {
+      if (ring == 2) epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, false, TLXCV_ACT_NONE, false, 2, false, N1>(a, lg, cgroup, lane);
+      else epilogue_loop<BLOCK_N, TLXCV_ACT_NONE, false, TLXCV_ACT_NONE, false, 4, false, N1>(a, lg, cgroup, lane);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
@@ -1146,6 +1508,9 @@ cudaError_t tc_conv_set_attributes() {
   if ((e = set_attr_t<256, kModeIm2col, false, true>()) != cudaSuccess) return e;
   if ((e = set_attr_t<128, kModeTiled, false, true>()) != cudaSuccess) return e;
   if ((e = set_attr_t<128, kModeIm2col, false, true>()) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_chain_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_chain_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
+  if ((e = cudaFuncSetAttribute(conv_chain_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   return cudaSuccess;
 }
 
@@ -1312,7 +1677,75 @@ std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloa
   return "";
 }
 
+bool tc_chain_supported(int Cin, int N1, int N2) {
+  return (N1 == 64 || N1 == 128) && Cin % 8 == 0 && Cin > 4 && N2 % 8 == 0 && N2 >= 64;
+}
+
+std::string tc_chain_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
+                             const __nv_bfloat16* w1, int K1tot, int N1, int R, int S, int stride, int pad, int dil,
+                             const __nv_bfloat16* w2, int N2, void* out_bf16, const void* residual_bf16) {
+  std::string err = load_driver_entry_points();
+  if (!err.empty()) return err;
+  memset(&L, 0, sizeof L);
+  if (!tc_chain_supported(Cin, N1, N2)) return "chain conv: unsupported channel counts";
+  ConvKernelParams& p = L.p;
+  const int P = (H + 2 * pad - dil * (R - 1) - 1) / stride + 1;
+  const int Q = (W + 2 * pad - dil * (S - 1) - 1) / stride + 1;
+  const long long M = static_cast<long long>(N) * P * Q;
+  if (M <= 0 || M > 0x7fffffffLL) return "conv: output pixel count out of range";
+  constexpr int block_n = 128;
+  p.M = static_cast<int>(M), p.Cout = N2;
+  p.S = S, p.R = R, p.P = P, p.Q = Q, p.H = H, p.W = W, p.stride = stride, p.pad = pad, p.dil = dil;
+  p.kb_per_tap = (Cin + kBlockK - 1) / kBlockK;
+  p.num_kb1 = R * S * p.kb_per_tap;
+  p.num_kb = p.num_kb1 + N1 / kBlockK;
+  if (K1tot != p.num_kb1 * kBlockK) return "chain conv: packed weight K does not match the kernel's K blocking";
+  p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  p.n_tiles = (N2 + block_n - 1) / block_n;
+  p.epi_warps = kEpiWarps;
+  p.sc_bufs = 2;
+  // resident first-conv weights (opt-in, TLXCV_CHAIN_W1RES=1): measured on B200 for the 64 -> 64 3x3 + 64 -> 256 chain at
+  // 56x56, bs256: 227 us resident against 219 us streamed - the chain is paced by its epilogue warps, not by what the SM
+  // takes in, so the 72 KB of shared memory are better spent on operand stages
+  const int w1_bytes = p.num_kb1 * N1 * 128;
+  const bool w1res = N1 == 64 && w1_bytes <= 80 * 1024 && tuning_env("TLXCV_CHAIN_W1RES") != nullptr;
+  auto stages_of = [&](int ring) {
+    return N1 == 64 ? (w1res ? ChainCfg<64, true>::stages_for(ring, p.num_kb1) : ChainCfg<64, false>::stages_for(ring, p.num_kb1))
+                    : ChainCfg<128, false>::stages_for(ring, p.num_kb1);
+  };
+  p.ring = (residual_bf16 != nullptr && stages_of(4) >= 3) ? 4 : 2;
+  if (const char* e = tuning_env("TLXCV_DEBUG_RING")) p.ring = atoi(e) == 4 ? 4 : 2;
+  p.stages = stages_of(p.ring);
+  if (p.stages < 2) return "chain conv: not enough shared memory for the operand ring";
+  L.smem = N1 == 64 ? (w1res ? ChainCfg<64, true>::smem_bytes(p.ring, p.num_kb1) : ChainCfg<64, false>::smem_bytes(p.ring, p.num_kb1))
+                    : ChainCfg<128, false>::smem_bytes(p.ring, p.num_kb1);
+  L.mode = kModeIm2col, L.block_n = block_n, L.threads = kThreadsBase, L.chain_n1 = N1, L.chain_w1res = w1res ? 1 : 0;
+  L.grid = static_cast<int>(std::min<long long>(p.m_tiles, sm_count));
+  const int n2_pad = ((N2 + 255) / 256) * 256;
+  if (!(err = encode_2d(&L.tmapB, w1, K1tot, 256, static_cast<uint64_t>(K1tot) * 2, kBlockK, N1)).empty()) return err;
+  if (!(err = encode_2d(&L.tmapB2, w2, N1, n2_pad, static_cast<uint64_t>(N1) * 2, kBlockK, block_n)).empty()) return err;
+  if (!(err = encode_im2col(&L.tmapA, act_in, N, H, W, Cin, R, S, stride, pad, dil)).empty()) return err;
+  if (!(err = encode_2d(&L.tmapOut, out_bf16, N2, p.M, static_cast<uint64_t>(N2) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)).empty())
+    return err;
+  if (residual_bf16) {
+    if (!(err = encode_2d(&L.tmapRes, residual_bf16, N2, p.M, static_cast<uint64_t>(N2) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)).empty())
+      return err;
+    p.residual = static_cast<const __nv_bfloat16*>(residual_bf16);
+  } else {
+    L.tmapRes = L.tmapB;
+  }
+  L.tmapA2 = L.tmapB;
+  return "";
+}
+
+template <int N1, bool W1RES>
+cudaError_t launch_chain(const TcConvLaunch& L, cudaStream_t st) {
+  return launch_pdl(conv_chain_kernel<N1, W1RES>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapB2, L.tmapOut, L.tmapRes, L.p);
+}
+
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t st) {
+  if (L.chain_n1 == 64) return L.chain_w1res ? launch_chain<64, true>(L, st) : launch_chain<64, false>(L, st);
+  if (L.chain_n1 == 128) return launch_chain<128, false>(L, st);
   if (L.dual) return launch_t<128, kModeTiled, true>(L, st);
   if (L.two && L.block_n == 256)
     return L.mode == kModeTiled ? launch_t<256, kModeTiled, false, true>(L, st) : launch_t<256, kModeIm2col, false, true>(L, st);

@@ -67,6 +67,8 @@ struct TcConvLaunch {
   ConvKernelParams p;
   int mode, block_n, grid, threads, smem, dual;
   int two;  // launched as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2)
+  int chain_n1;  // > 0: chain launch (conv -> 1x1 conv in one kernel), width of the first conv (64 or 128)
+  int chain_w1res;  // chain launch keeps the first conv's weights resident in shared memory
 };
 
 // Encodes the TMA descriptors and picks tile shape; returns an empty string or an error message.
@@ -77,6 +79,12 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
 std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloat16* a1, int M, int K1,
                                  const __nv_bfloat16* w1, const __nv_bfloat16* a2, int N, int H2, int W2, int C2, int stride2,
                                  const __nv_bfloat16* w2, int Cout, void* out_bf16);
+// out = act2( bn2(conv1x1( relu(bn1(conv_RxS(in))) )) + residual ): first conv N1 = 64 / 128 channels wide, its output never leaves
+// the SM (conv_chain_kernel).  w1: im2col packing [256][K1tot]; w2: [N2 padded to 256][N1].
+std::string tc_chain_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* act_in, int N, int H, int W, int Cin,
+                             const __nv_bfloat16* w1, int K1tot, int N1, int R, int S, int stride, int pad, int dil,
+                             const __nv_bfloat16* w2, int N2, void* out_bf16, const void* residual_bf16);
+bool tc_chain_supported(int Cin, int N1, int N2);
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
 cudaError_t tc_conv_set_attributes();
 // number of K elements per output channel in the packed weight matrix for this geometry

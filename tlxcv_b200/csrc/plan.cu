@@ -46,6 +46,9 @@ struct OpRt {
   bool nop = false;           // fused into another op: no launch, no tensors of its own
   int dual_a = -1;            // index of the 1x1 conv whose output was this conv's residual and now runs as the
                               // first accumulator of this op's dual-GEMM kernel (-1: none)
+  int chain_mid = -1;         // chain kernel: the (elided) tensor between the two convs; the op's in0 is rewired to the first conv's input
+  int chain_a = -1;           // 1x1 conv: index of the conv that produced its input and now runs as the first GEMM of this op's
+                              // chain kernel (-1: none)
   int fused_argmax = -1;      // Linear: index of the ARGMAX op over its logits that runs inside this launch (-1: none)
   bool skip_logits = false;   // ... and nothing else reads the logits: they are never written
   unsigned long long* amax_keys = nullptr;  // fused argmax scratch (owned, zero between launches)
@@ -330,6 +333,53 @@ int compile_conv_dual(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
   const double bytes = (static_cast<double>(M) * (K1 + C2 + K) + static_cast<double>(K) * (K1 + C2)) * 2;
   set_info(op, "conv_tcgen05_dual_n128", 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.tc.grid, op.tc.threads, op.tc.smem,
            op.tc.block_n);
+  return TLXCV_OK;
+}
+
+// B = a 1x1 conv (+ BN, + residual, + ReLU), A = the conv (+ BN + ReLU) whose N1 = 64 / 128-channel output is B's only input:
+// ONE kernel, the intermediate stays in shared memory (conv_chain_kernel)
+int compile_conv_chain(tlxcv_plan* p, OpRt& op, cudaStream_t st) {
+  tlxcv_ctx* ctx = p->ctx;
+  const tlxcv_op_desc& d = op.d;
+  const tlxcv_op_desc& a = p->ops[op.chain_a].d;
+  const TensorRt& xin = p->tensors[a.in0];
+  const TensorRt& mid = p->tensors[op.chain_mid];
+  const TensorRt& out = p->tensors[d.out];
+  const int N = xin.d.n, H = xin.d.h, W = xin.d.w, C = xin.d.c, N1 = mid.d.c, N2 = out.d.c;
+  if (!d.filters || !a.filters) return fail(ctx, TLXCV_ERR_INVALID, "op conv: filters pointer is NULL");
+  const int N2_pad = static_cast<int>(align_up(N2, 256));
+  int rc;
+  if ((rc = dev_alloc(p, &op.scale, N2_pad)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.shift, N2_pad)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.scale2, 256)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &op.shift2, 256)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, fold_bn(op.scale, op.shift, d.bn_gamma, d.bn_beta, d.bn_mean, d.bn_var, d.bias, d.bn_eps, N2, N2_pad, st));
+  TLX_CUDA(ctx, fold_bn(op.scale2, op.shift2, a.bn_gamma, a.bn_beta, a.bn_mean, a.bn_var, a.bias, a.bn_eps, N1, 256, st));
+  const int K1 = tc_conv_packed_k(C, a.r, a.s, 1, kModeIm2col);
+  __nv_bfloat16 *w1 = nullptr, *w2 = nullptr;
+  if ((rc = dev_alloc(p, &w1, static_cast<size_t>(256) * K1)) != TLXCV_OK) return rc;
+  if ((rc = dev_alloc(p, &w2, static_cast<size_t>(N2_pad) * N1)) != TLXCV_OK) return rc;
+  TLX_CUDA(ctx, pack_conv_weights(a.filters, w1, N1, 256, C, a.r, a.s, 1, kModeIm2col, K1, st));
+  TLX_CUDA(ctx, pack_conv_weights(d.filters, w2, N2, N2_pad, N1, 1, 1, 1, kModeTiled, N1, st));
+  op.weights = w1;
+  const void* res = d.in1 >= 0 ? p->arena + p->tensors[d.in1].offset : nullptr;
+  std::string err = tc_chain_prepare(op.tc, ctx->sm_count, reinterpret_cast<const __nv_bfloat16*>(p->arena + xin.offset), N, H, W, C, w1,
+                                     K1, N1, a.r, a.s, a.stride, a.pad, a.dil, w2, N2, p->arena + out.offset, res);
+  if (!err.empty()) return fail(ctx, TLXCV_ERR_UNSUPPORTED, "%s", err.c_str());
+  ConvKernelParams& kp = op.tc.p;
+  kp.scale = op.scale, kp.shift = op.shift, kp.scale2 = op.scale2, kp.shift2 = op.shift2;
+  kp.act1 = d.act1, kp.alpha1 = d.alpha1, kp.act2 = d.act2, kp.alpha2 = d.alpha2;
+  kp.out_f32 = 0;
+  op.impl = kImplTcConv;
+  const double M = static_cast<double>(out.d.n) * out.d.h * out.d.w;
+  const double flops = 2.0 * M * (static_cast<double>(N1) * C * a.r * a.s + static_cast<double>(N2) * N1);
+  const double th = std::min<double>(H, (out.d.h - 1.0) * a.stride + (a.r - 1) * a.dil + 1);
+  const double tw = std::min<double>(W, (out.d.w - 1.0) * a.stride + (a.s - 1) * a.dil + 1);
+  const double bytes = (static_cast<double>(N) * th * tw * C + static_cast<double>(N1) * C * a.r * a.s + static_cast<double>(N2) * N1 +
+                        M * N2 * (d.in1 >= 0 ? 2 : 1)) * 2;
+  char name[48];
+  snprintf(name, sizeof name, "conv_chain_%dx%d_n%d_to_1x1", a.r, a.s, N1);
+  set_info(op, name, 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.tc.grid, op.tc.threads, op.tc.smem, 128);
   return TLXCV_OK;
 }
 
@@ -798,6 +848,49 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       B.d.in1 = -1;
     }
   }
+  // ---- pre-pass: conv (+BN+ReLU) -> 1x1 conv (+BN, +residual, +ReLU) whose 64 / 128-channel intermediate has no other reader
+  //      (conv2 -> conv3 of a ResNet bottleneck, classification/resnet.py:146-155): ONE chain kernel, the intermediate
+  //      never reaches HBM and the MMA-bound 3x3 runs under the 1x1's output traffic ----
+  if (!p->f32 && !tuning_env("TLXCV_NO_CHAIN")) {
+    const int max_n1 = tuning_env("TLXCV_CHAIN_MAX_N1") ? atoi(tuning_env("TLXCV_CHAIN_MAX_N1")) : 128;
+    for (int i = 0; i < n_ops; ++i) {
+      OpRt& B = p->ops[i];
+      const tlxcv_op_desc& d = B.d;
+      if (B.nop || B.dual_a >= 0 || d.kind != TLXCV_OP_CONV) continue;
+      if (d.r != 1 || d.s != 1 || d.stride != 1 || d.pad != 0 || d.dil != 1 || d.groups != 1) continue;
+      const bool res = d.in1 >= 0;
+      if (res ? (d.act1 != TLXCV_ACT_NONE || (d.act2 != TLXCV_ACT_NONE && d.act2 != TLXCV_ACT_RELU))
+              : ((d.act1 != TLXCV_ACT_NONE && d.act1 != TLXCV_ACT_RELU) || d.act2 != TLXCV_ACT_NONE))
+        continue;
+      const TensorRt& T = p->tensors[d.in0];
+      const TensorRt& o = p->tensors[d.out];
+      if (T.d.role != TLXCV_ROLE_INTERNAL || T.d.dtype != TLXCV_ACT || o.d.role != TLXCV_ROLE_INTERNAL || o.d.dtype != TLXCV_ACT) continue;
+      if (d.in1 == d.in0 || o.cs != o.d.c || T.d.c > max_n1) continue;
+      if (res && (p->tensors[d.in1].d.role != TLXCV_ROLE_INTERNAL || p->tensors[d.in1].d.dtype != TLXCV_ACT)) continue;
+      int producer = -1, users = 0;
+      for (int k = 0; k < n_ops; ++k) {
+        if (p->ops[k].nop) continue;
+        if (p->ops[k].d.out == d.in0) producer = k;
+        if (p->ops[k].d.in0 == d.in0 || p->ops[k].d.in1 == d.in0) ++users;
+      }
+      if (producer < 0 || producer >= i || users != 1) continue;
+      OpRt& A = p->ops[producer];
+      const tlxcv_op_desc& a = A.d;
+      if (A.use_stem || A.dual_a >= 0 || A.chain_a >= 0 || a.kind != TLXCV_OP_CONV || a.in1 >= 0 || a.groups != 1) continue;
+      if (a.act1 != TLXCV_ACT_RELU || a.act2 != TLXCV_ACT_NONE || a.r > 3 || a.s > 3) continue;
+      const TensorRt& x = p->tensors[a.in0];
+      if (x.d.role != TLXCV_ROLE_INTERNAL || x.d.dtype != TLXCV_ACT || x.cs != x.d.c) continue;
+      if (!tc_chain_supported(x.d.c, T.d.c, o.d.c)) continue;
+      // the chain kernel's first GEMM loads its operands by im2col TMA (every pixel 9 times from L2 for a 3x3): worth it
+      // when the 1x1 that follows is wide enough to be the longer half (the epilogue / HBM traffic hides the rest)
+      if (o.d.c < 2 * T.d.c && !tuning_env("TLXCV_FORCE_CHAIN")) continue;
+      p->tensors[d.in0].elided = true;
+      A.nop = true;
+      B.chain_a = producer;
+      B.chain_mid = d.in0;
+      B.d.in0 = a.in0;  // the chain kernel reads the first conv's input
+    }
+  }
   // ---- pre-pass: `argmax(linear(x))` (ImageClassification.predict, tasks/image_classification.py:20-23): the argmax runs
   //      inside the Linear launch (per-row 64-bit atomicMax keys, decoded by the last CTA); logits nobody else reads are
   //      never written ----
@@ -880,7 +973,8 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     int rc = TLXCV_OK;
     if (op.nop) {
       op.impl = kImplNop;
-      set_info(op, d.kind == TLXCV_OP_CONV ? "(first GEMM of the dual conv)"
+      set_info(op, d.kind == TLXCV_OP_CONV ? (p->tensors[d.out].elided && [&] { for (const OpRt& q : p->ops) if (q.chain_a == i) return true; return false; }()
+                                                  ? "(first GEMM of the chain conv)" : "(first GEMM of the dual conv)")
                                            : (d.kind == TLXCV_OP_ARGMAX ? "(fused into the linear launch)" : "(fused into the stem conv)"),
                0, 0, 0, 0, 0, 0, 0, 0);
       continue;
@@ -920,7 +1014,9 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         break;
       case TLXCV_OP_CONV:
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_ACT) return fail(ctx, TLXCV_ERR_INVALID, "op %d: conv tensors must be activations", i);
-        rc = op.use_stem ? compile_stem(p, op, st) : (op.dual_a >= 0 ? compile_conv_dual(p, op, st) : compile_conv(p, op, st, false));
+        rc = op.use_stem ? compile_stem(p, op, st)
+                         : (op.dual_a >= 0 ? compile_conv_dual(p, op, st)
+                                           : (op.chain_a >= 0 ? compile_conv_chain(p, op, st) : compile_conv(p, op, st, false)));
         break;
       case TLXCV_OP_LINEAR:
         if (in.d.dtype != TLXCV_ACT || o.d.dtype != TLXCV_F32 || in.d.h != 1 || in.d.w != 1)
