@@ -35,7 +35,7 @@ METRIC = "resnet50_bs256_images_per_sec"
 UNIT = "images/s"
 
 
-TENSOR_KERNELS = ("conv_tcgen05", "conv3x3_slab", "stem_rowring")
+TENSOR_KERNELS = ("conv_tcgen05", "conv_chain", "conv3x3_slab", "stem_rowring")
 
 
 def load_ncu_traffic():
@@ -317,7 +317,7 @@ def roofline_report(prof, ms_per_step, peaks):
     return {
         "bound": "tensor", "achieved": achieved, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
         "frac": achieved / peaks["bf16_tflops"], "traffic": load_ncu_traffic(), "peak_source": peaks["source"],
-        "kernel": "tcgen05 conv family: conv_tcgen05_* / conv3x3_slab / stem_rowring (all conv + fc launches of a step)",
+        "kernel": "tcgen05 conv family: conv_tcgen05_* / conv_chain_* / conv3x3_slab / stem_rowring (all conv + fc launches of a step)",
         "launches_per_step": len(conv), "flops_per_step": flops, "kernel_ms_per_step": conv_ms,
         "share_of_step": conv_ms / ms_per_step,
         "how": "per-op CUDA-event times of a profiling run, rescaled so that all ops sum to the graph-timed ms_per_step",
@@ -339,6 +339,8 @@ def main():
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak: 256 images per GPU (default); strong: a global batch of 256 split over the GPUs")
     ap.add_argument("--sustained-seconds", type=float, default=2.5)
+    ap.add_argument("--quick", action="store_true",
+                    help="device-resident loop + parity only (the short command the ncu passes of tools/ncu_round.sh wrap)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-gpu-library-baseline", action="store_true")
     args = ap.parse_args()
@@ -348,6 +350,9 @@ def main():
         args.warmup = 2 if args.impl == "reference" else 10
     if args.impl != "reference":
         args.warmup = max(args.warmup, 3)
+    if args.quick:
+        args.no_cpu_baseline = args.no_gpu_library_baseline = True
+        args.sustained_seconds = 0.0
 
     # stdout carries exactly ONE line, the JSON result: everything libraries print while the run lasts (NCCL's version
     # banner at NCCL_DEBUG >= VERSION, torch warnings) goes to stderr; emit() writes the result to the real stdout
@@ -474,6 +479,16 @@ def main():
 
     # three slots: the H2D engine never waits for a forward to release a slot (154 MB per step is within ~20 % of what this
     # box's PCIe link moves in one forward time, so any bubble in the copy stream shows up in the step)
+    if args.quick:
+        if rank == 0:
+            prof = plan.profile([x_dev], og.local[0])
+            emit({"metric": METRIC, "value": world * per_gpu / ms_per_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                  "warmup": args.warmup, "ms_per_step": ms_per_step, "quick": True, "parity": parity,
+                  "roofline": roofline_report(prof, ms_per_step, peaks), "launches_per_step": plan.num_launches,
+                  "clocks": sampler.stop()})
+        if world > 1:
+            tdist.destroy_process_group()
+        return 0
     pipe = HostPipeline(model, tuple(x_host.shape), depth=3, device=device, gather=gather, gather_to="rank0")
     e2e_ms, e2e_d2h = run_e2e(pipe, x_host)
     last = out_host[(args.steps - 1) % 2]

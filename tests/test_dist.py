@@ -57,3 +57,23 @@ def test_gather_rows_world2_gloo(n_total):
         assert p.exitcode == 0
     assert sorted(r[0] for r in results) == [0, 1]
     assert all(r[1] and r[2] and r[3] for r in results)
+
+
+def test_pin_rank_affinity_gives_disjoint_core_slices():
+    from tlxcv_b200.dist import pin_rank_affinity
+
+    if not hasattr(os, "sched_getaffinity"):
+        pytest.skip("no sched_getaffinity here")
+    saved = os.sched_getaffinity(0)
+    try:
+        cores = sorted(saved)
+        if len(cores) < 2:
+            pytest.skip("needs two host cores")
+        a = pin_rank_affinity(0, 2)
+        os.sched_setaffinity(0, saved)
+        b = pin_rank_affinity(1, 2)
+        assert a and b and not set(a) & set(b) and set(a) | set(b) <= set(cores)
+        os.sched_setaffinity(0, saved)
+        assert pin_rank_affinity(0, 1) == cores           # a single rank keeps everything
+    finally:
+        os.sched_setaffinity(0, saved)

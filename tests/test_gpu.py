@@ -290,10 +290,11 @@ def test_bottleneck_tail_and_downsample_run_as_one_dual_gemm_kernel(cin, mid, co
         del os.environ["TLXCV_FORCE_DUAL"]
     assert "conv_tcgen05_dual_n128" in kernels, kernels
     os.environ["TLXCV_NO_DUAL"] = "1"
+    os.environ["TLXCV_NO_CHAIN"] = "1"      # otherwise conv2 -> conv3 (+ the downsample map as residual) becomes a chain kernel
     try:
         unfused, kernels2, launches2 = run()
     finally:
-        del os.environ["TLXCV_NO_DUAL"]
+        del os.environ["TLXCV_NO_DUAL"], os.environ["TLXCV_NO_CHAIN"]
     assert "conv_tcgen05_dual_n128" not in kernels2 and launches2 == launches + 1
     q = lambda t: t.bfloat16().float()
     bn = lambda t, b: F.batch_norm(t, b["moving_mean"], b["moving_var"], b["gamma"], b["beta"], False, 0.0, 1e-5)
@@ -556,6 +557,18 @@ def test_weight_update_rebuilds_the_plan():
         m.fc.biases.add_(1.0)
     b = m(x)
     assert float((b - a - 1.0).abs().max()) < 1e-5
+
+
+def test_in_place_data_updates_need_invalidate_plans():
+    """Writes through p.data do not bump the version counter the plan cache watches: invalidate_plans() is the documented way."""
+    from tlxcv_b200 import models
+
+    m = models.resnet18().cuda().set_eval()
+    x = torch.randn(2, 3, 64, 64, device="cuda")
+    a = m(x)
+    m.fc.biases.data.add_(1.0)
+    m.invalidate_plans()
+    assert float((m(x) - a - 1.0).abs().max()) < 1e-5
 
 
 def test_uint8_preprocessing_fused_into_the_input_kernel():

@@ -139,9 +139,20 @@ class Module(torch.nn.Module):
         else:
             raise ValueError(f"unsupported weight format {fmt!r} (npz | npz_dict)")
 
+    def invalidate_plans(self):
+        """Drop every cached B200 plan under this module, so that the next call re-reads the parameters.
+
+        Plans pack bf16 copies of the weights at build time and are rebuilt automatically when a parameter's
+        ``(data_ptr, _version)`` changes - which in-place writes through ``p.data`` (``p.data.copy_(w)``, EMA updates) do
+        NOT touch.  Call this after such updates."""
+        for m in self.modules():
+            m.__dict__.pop("_b200_plans", None)
+        return self
+
     def load_weights(self, file_path, format=None, skip=False):
         fmt = format or _format_of(file_path)
-        data = np.load(file_path, allow_pickle=True)
+        # the positional .npz format stores an object array of per-tensor arrays (needs pickle); named files do not
+        data = np.load(file_path, allow_pickle=(fmt == "npz"))
         if fmt == "npz":
             arrays = list(data["params"])
             weights = self.all_weights
@@ -150,6 +161,7 @@ class Module(torch.nn.Module):
             with torch.no_grad():
                 for p, a in zip(weights, arrays):
                     p.copy_(_fit(torch.from_numpy(np.asarray(a, dtype=np.float32)), p.shape))
+            self.invalidate_plans()
         elif fmt == "npz_dict":
             sd = {k: torch.from_numpy(data[k]) for k in data.files}
             self.load_state_dict(sd, strict=not skip)

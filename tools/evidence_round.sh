@@ -1,7 +1,7 @@
 #!/bin/bash
 # Round-end evidence (run under gpurun, 1 GPU): GPU parity suite, bench + ncu passes (tools/ncu_round.sh), per-op profiles
 # of every BASELINE config.  Everything lands in gpurun_out/; tools/ncu_summary.py + a copy into profiles/ follow on the host.
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_${TAG}.log 2>&1; echo "pytest rc=$?"
 tail -2 gpurun_out/pytest_gpu_${TAG}.log
@@ -15,3 +15,5 @@ prof mobilenet_v1 512 224
 prof darknet53_det 64 608
 prof darknet53_cls 256 224
 prof resnet18 256 224
+prof yolov3_darknet53 64 608
+prof mobilenet_v1_det 256 300

@@ -4,6 +4,7 @@
 //   mode 2: st.global.v4 from smem, 64 B row segments (8 rows per instruction)
 //   mode 3: st.global.v4 from smem, 128 B row segments (4 rows per instruction)
 //   mode 4: TMA store, 128 rows x 64 cols issued by one thread per CTA (16 KB boxes)
+//   mode 5: st.global.v4 straight from registers, every lane its own row's 64 B (4 instructions per 32 x 32 item, rows C*2 bytes apart)
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o store_bw store_bw.cu -lcuda
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -21,7 +22,7 @@ __global__ void __launch_bounds__(256, 1) store_kernel(const __grid_constant__ C
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int lg = warp & 3, half = warp >> 2;
-  constexpr int W = (MODE == 0 || MODE == 2) ? 32 : 64;       // columns per item
+  constexpr int W = (MODE == 0 || MODE == 2 || MODE == 5) ? 32 : 64;       // columns per item
   constexpr int ROWB = W * 2;
   uint8_t* stg = smem + warp * 8192;                          // 2 buffers x 4 KB
   uint32_t nstore = 0;
@@ -48,6 +49,15 @@ __global__ void __launch_bounds__(256, 1) store_kernel(const __grid_constant__ C
     for (int it = 0; it < items_per_tile; ++it) {
       const int cbase = half * (C / 2) + it * W;
       uint8_t* buf = stg + (nstore & 1) * 4096;
+      if (MODE == 5) {
+        if (m0 + lane < M) {
+          uint4* dst = reinterpret_cast<uint4*>(out + (size_t)(m0 + lane) * C + cbase);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) dst[j] = make_uint4(tile, it, lane, j);
+        }
+        ++nstore;
+        continue;
+      }
       if (MODE <= 1) {
         if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         __syncwarp();
@@ -109,8 +119,9 @@ int main(int argc, char** argv) {
   const int m_tiles = (M + 127) / 128;
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0), cudaEventCreate(&e1);
-  const char* names[] = {"tma 32x32 (64B rows)", "tma 32x64 (128B rows)", "stg 64B segments", "stg 128B segments", "tma 128x64 per CTA"};
-  for (int mode = 0; mode < 5; ++mode) {
+  const char* names[] = {"tma 32x32 (64B rows)", "tma 32x64 (128B rows)", "stg 64B segments", "stg 128B segments", "tma 128x64 per CTA",
+                         "stg per-lane rows (regs)"};
+  for (int mode = 0; mode < 6; ++mode) {
     CUtensorMap tm = mode == 0 ? make(32, 32, CU_TENSOR_MAP_SWIZZLE_64B) : (mode == 4 ? make(64, 128, CU_TENSOR_MAP_SWIZZLE_128B) : make(64, 32, CU_TENSOR_MAP_SWIZZLE_128B));
     auto launch = [&]() {
       switch (mode) {
@@ -119,6 +130,7 @@ int main(int argc, char** argv) {
         case 2: store_kernel<2><<<148, 256, 65536>>>(tm, out, M, C, m_tiles); break;
         case 3: store_kernel<3><<<148, 256, 65536>>>(tm, out, M, C, m_tiles); break;
         case 4: store_kernel<4><<<148, 256, 65536>>>(tm, out, M, C, m_tiles); break;
+        case 5: store_kernel<5><<<148, 256, 65536>>>(tm, out, M, C, m_tiles); break;
       }
     };
     cudaFuncSetAttribute(store_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
@@ -126,6 +138,7 @@ int main(int argc, char** argv) {
     cudaFuncSetAttribute(store_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(store_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     cudaFuncSetAttribute(store_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+    cudaFuncSetAttribute(store_kernel<5>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
     for (int i = 0; i < 3; ++i) launch();
     cudaEventRecord(e0);
     for (int i = 0; i < 10; ++i) launch();

@@ -77,7 +77,7 @@ def traffic_json(path, out_json):
         v = float(r["Metric Value"].replace(",", ""))
         scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(r["Metric Unit"], 1.0)
         d[r["Metric Name"]] = v * scale
-    fam = ("conv_tcgen05", "conv3x3_slab", "stem_rowring")
+    fam = ("conv_tcgen05", "conv_chain", "conv3x3_slab", "stem_rowring")
     ids = list(per.values())
     # one step = the launches between two consecutive import kernels
     starts = [i for i, d in enumerate(ids) if d["kernel"].startswith("import_nchw")]
