@@ -1,18 +1,21 @@
 #!/usr/bin/env python
 """Headline benchmark: ResNet-50 bs256 224x224 bf16 inference, images/s (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong] [--quick]
 
-One process per GPU (torchrun env for N > 1).  Per-GPU batch is fixed at 256 (weak scaling: the
-global batch is 256*N, sharded one contiguous block per rank, logits all-gathered over NCCL every
-step).  A step = one forward of the sharded batch through tlxcv_b200 (+ the gather).
+One process per GPU (torchrun env for N > 1).  Per-GPU batch is fixed at 256 (weak scaling: the global batch is 256*N,
+sharded one contiguous block per rank; the logits all-gather of step i-1 runs on a side stream under forward i);
+`--scaling strong` splits a global batch of 256 instead (also reported as `strong_scaling` in every weak run at N > 1).
+A step = one forward of the sharded batch of DISTINCT synthetic images through tlxcv_b200 (+ the gather).
 
-JSON line (rank 0): `value` = whole-job images/s with inputs resident in HBM; `e2e` = the same
-through the host-buffer API (pinned host batch -> H2D -> forward -> gather -> D2H logits, double
-buffered); `roofline` = the conv tcgen05 kernel family, FLOPs / CUDA-event time measured live;
-`cpu_baseline` = the oracle restatement of the reference forward on this box's host cores.
-`--impl reference` times that CPU path alone (tensorlayerx itself is not installable; the oracle
-is the reference's model code over torch.nn.functional — see oracle/__init__.py).
+JSON line (rank 0): `value` = whole-job images/s with inputs resident in HBM; `sustained` = the same over >= 2.5 s;
+`e2e` = through the host-buffer API (pinned host batch -> H2D -> forward -> gather -> D2H logits, three streams) with the
+box's own H2D ceiling beside it; `parity` = the timed batch's first 32 images against the CPU oracle; `roofline` = the conv
+tcgen05 kernel family inside the timed region, split into tensor-bound and HBM-bound layers; `cpu_baseline` = the oracle
+restatement of the reference forward on this box's host cores; `gpu_library_baseline` = the reference's math on cuDNN
+(eager fp32 / bf16, and BN-folded bf16 CUDA-graphed).  `--impl reference` times the CPU path alone on full 256-image
+batches (tensorlayerx itself is not installable; the oracle is the reference's model code over torch.nn.functional - see
+oracle/__init__.py).
 """
 from __future__ import annotations
 
