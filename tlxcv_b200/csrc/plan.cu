@@ -44,6 +44,7 @@ struct OpRt {
   bool use_stem = false;      // row-ring stem kernel chosen in the pre-pass
   int pool_op = -1;           // index of the max-pool op fused into this stem (-1: none)
   bool nop = false;           // fused into another op: no launch, no tensors of its own
+  bool chain_first = false;   // ... as the first GEMM of a chain kernel (report only)
   int dual_a = -1;            // index of the 1x1 conv whose output was this conv's residual and now runs as the
                               // first accumulator of this op's dual-GEMM kernel (-1: none)
   int chain_mid = -1;         // chain kernel: the (elided) tensor between the two convs; the op's in0 is rewired to the first conv's input
@@ -886,6 +887,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
       if (o.d.c < 2 * T.d.c && !tuning_env("TLXCV_FORCE_CHAIN")) continue;
       p->tensors[d.in0].elided = true;
       A.nop = true;
+      A.chain_first = true;
       B.chain_a = producer;
       B.chain_mid = d.in0;
       B.d.in0 = a.in0;  // the chain kernel reads the first conv's input
@@ -973,8 +975,7 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
     int rc = TLXCV_OK;
     if (op.nop) {
       op.impl = kImplNop;
-      set_info(op, d.kind == TLXCV_OP_CONV ? (p->tensors[d.out].elided && [&] { for (const OpRt& q : p->ops) if (q.chain_a == i) return true; return false; }()
-                                                  ? "(first GEMM of the chain conv)" : "(first GEMM of the dual conv)")
+      set_info(op, d.kind == TLXCV_OP_CONV ? (op.chain_first ? "(first GEMM of the chain conv)" : "(first GEMM of the dual conv)")
                                            : (d.kind == TLXCV_OP_ARGMAX ? "(fused into the linear launch)" : "(fused into the stem conv)"),
                0, 0, 0, 0, 0, 0, 0, 0);
       continue;
