@@ -1274,7 +1274,7 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     a.first_tile = worker, a.tile_stride = n_workers;
     a.two = 0, a.rank = 0, a.tmem_empty_remote = 0;
     a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
-    a.ablate = 0;
+    a.ablate = p.ablate;
     a.trace = nullptr;
     a.chain_m_tiles = m_tiles;
     a.acc1_full_bar = smem_u32(acc1_full_bar), a.acc1_empty_bar = smem_u32(acc1_empty_bar);
@@ -1704,6 +1704,7 @@ std::string tc_chain_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16*
   p.n_tiles = (N2 + block_n - 1) / block_n;
   p.epi_warps = kEpiWarps;
   p.sc_bufs = 2;
+  if (const char* e = debug_env("TLXCV_DEBUG_ABLATE")) p.ablate = atoi(e);  // timing experiments only (debug build): results are wrong
   // resident first-conv weights (opt-in, TLXCV_CHAIN_W1RES=1): measured on B200 for the 64 -> 64 3x3 + 64 -> 256 chain at
   // 56x56, bs256: 227 us resident against 219 us streamed - the chain is paced by its epilogue warps, not by what the SM
   // takes in, so the 72 KB of shared memory are better spent on operand stages
