@@ -19,6 +19,7 @@
  *   nn.GroupConv2d + nn.BatchNorm2d + nn.ReLU/ReLU6/LeakyReLU + add TLXCV_OP_CONV
  *   nn.MaxPool2d                                                    TLXCV_OP_MAXPOOL
  *   nn.AdaptiveAvgPool2d(1)                                         TLXCV_OP_GAP
+ *   nn.AvgPool2d(2, 2)   segmentation/backbones/resnet_vd.py:25-27  TLXCV_OP_AVGPOOL
  *   nn.Linear                                                       TLXCV_OP_LINEAR
  *   tlx.losses.softmax_cross_entropy_with_logits  tasks/image_classification.py:14  TLXCV_OP_SOFTMAX_CE
  *   Interpolater (nearest x2) + tlx.concat  detection/yolov3.py:244,252  TLXCV_OP_UPSAMPLE_CONCAT
@@ -84,6 +85,7 @@ typedef enum {
                                  times (in1 = -1: up-sampling alone; r = s = 1: channel concat): Interpolater +
                                  tlx.concat of YOLOv3FPN.forward (detection/yolov3.py:244,252-253) in one pass          */
   TLXCV_OP_SOFTMAX = 10,     /* (N, K) fp32 logits -> (N, K) fp32 probabilities (softmax over the class axis)           */
+  TLXCV_OP_AVGPOOL = 12,     /* AvgPool2d(k, stride) without padding (ResNet_vd shortcut, segmentation/backbones/resnet_vd.py:25-27) */
   TLXCV_OP_SOFTMAX_CE = 11   /* in0 = (N, K) fp32 logits, in1 = (N) int64 labels -> (1) fp32 mean cross-entropy:
                                  tlx.losses.softmax_cross_entropy_with_logits (tasks/image_classification.py:10-15)        */
 } tlxcv_op_kind;

@@ -116,6 +116,36 @@ def _build_yolov3(shim=None, **kw):
         return YOLOv3Net()
 
 
+def _build_resnet_vd(shim=None, **kw):
+    """segmentation/backbones/resnet_vd.py with ITS OWN helper files (`from ..layers import Activation, Add`): the helpers
+    are loaded one by one from segmentation/layers/activation.py and wrap_functions.py; the package's __init__ (which also
+    pulls in the pyramid-pooling / JPU layers of the segmentation heads) is not executed."""
+    import types
+
+    shim = shim or tlx_compat.installed
+    seg = os.path.join(REFERENCE_ROOT, "tlxcv", "models", "segmentation")
+    with shim():
+        created = []
+        try:
+            for name, path in ((_PKG, os.path.join(REFERENCE_ROOT, "tlxcv")), (_PKG + ".models", os.path.join(REFERENCE_ROOT, "tlxcv", "models")),
+                               (_PKG + ".models.segmentation", seg), (_PKG + ".models.segmentation.backbones", os.path.join(seg, "backbones")),
+                               (_PKG + ".models.segmentation.layers", os.path.join(seg, "layers"))):
+                m = types.ModuleType(name)
+                m.__path__, m.__package__ = [path], name
+                sys.modules[name] = m
+                created.append(name)
+            layers = sys.modules[_PKG + ".models.segmentation.layers"]
+            for fname, names in (("activation", ("Activation",)), ("wrap_functions", ("Add",))):
+                sub = importlib.import_module(f"{_PKG}.models.segmentation.layers.{fname}")
+                for n in names:
+                    setattr(layers, n, getattr(sub, n))
+            mod = importlib.import_module(_PKG + ".models.segmentation.backbones.resnet_vd")
+            return mod.ResNet_vd(**kw)
+        finally:
+            for k in [k for k in sys.modules if k == _PKG or k.startswith(_PKG + ".")]:
+                del sys.modules[k]
+
+
 def _build_det_mobilenet(shim=None, **kw):
     m = load_reference_package_module("models.detection.backbones.mobilenet_v1", shim)
     shim = shim or tlx_compat.installed
@@ -139,7 +169,8 @@ MODELS = {
 }
 
 
-PACKAGE_MODELS = {"yolov3_darknet53": _build_yolov3, "mobilenet_v1_det": _build_det_mobilenet}
+PACKAGE_MODELS = {"yolov3_darknet53": _build_yolov3, "mobilenet_v1_det": _build_det_mobilenet,
+                  "resnet50_vd": _build_resnet_vd, "resnet18_vd": lambda shim=None, **kw: _build_resnet_vd(shim, layers=18, **kw)}
 
 
 def build(name: str, shim=None, **kwargs):

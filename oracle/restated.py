@@ -323,6 +323,43 @@ def mobilenet_v1_det(sd, inputs, feature_maps=(4, 6, 13), taps=None):
     return outs
 
 
+def resnet_vd(sd, x, layers=50, output_stride=8, taps=None):
+    """segmentation/backbones/resnet_vd.py:315-326 (ConvBNLayer :44-50, BottleneckBlock :103-113, BasicBlock :160-169,
+    stage table :222-311)."""
+    p = _P(sd, "", taps)
+    depth = {18: [2, 2, 2, 2], 34: [3, 4, 6, 3], 50: [3, 4, 6, 3], 101: [3, 4, 23, 3]}[layers]
+    dil = {8: {2: 2, 3: 4}, 16: {3: 2}}.get(output_stride, {})
+
+    def cbl(q, x, k, stride=1, dilation=1, vd=False, act=None):
+        if vd:
+            x = F.avg_pool2d(x, 2, 2)                                   # :45-46
+        y = bn(q.sub("batch_norm"), conv(q.sub("_conv"), x, stride, (k - 1) // 2 if dilation == 1 else dilation, 1, dilation))
+        return F.relu(y) if act == "relu" else y
+
+    y = cbl(p.sub("conv1_1"), x, 3, 2, act="relu")
+    y = cbl(p.sub("conv1_2"), y, 3, act="relu")
+    y = cbl(p.sub("conv1_3"), y, 3, act="relu")
+    y = F.max_pool2d(y, 3, 2, 1)
+    feats = []
+    for block in range(4):
+        for i in range(depth[block]):
+            rate = dil.get(block, 1)
+            stride = 2 if i == 0 and block != 0 and rate == 1 else 1
+            bp = p.sub(f"stage_list.{block}.{i}")
+            vd = i == 0 and not (block == 0 or stride == 1)             # short: is_vd_mode = not (if_first or stride == 1)
+            if layers >= 50:
+                t = cbl(bp.sub("conv0"), y, 1, act="relu")
+                t = cbl(bp.sub("conv1"), t, 3, stride, rate, act="relu")
+                t = cbl(bp.sub("conv2"), t, 1)
+            else:
+                t = cbl(bp.sub("conv0"), y, 3, stride, rate, act="relu")
+                t = cbl(bp.sub("conv1"), t, 3, 1, rate)
+            short = y if i != 0 else cbl(bp.sub("short"), y, 1, 1, 1, vd)
+            y = bp.tap(F.relu(short + t))
+        feats.append(y)
+    return feats
+
+
 FORWARD = {
     "resnet18": lambda sd, x, **k: resnet(sd, x, 18, **k),
     "resnet34": lambda sd, x, **k: resnet(sd, x, 34, **k),
@@ -337,6 +374,8 @@ FORWARD = {
     "darknet53_det": darknet53_det,
     "yolov3_darknet53": yolov3_darknet53,
     "mobilenet_v1_det": mobilenet_v1_det,
+    "resnet50_vd": lambda sd, x, **k: resnet_vd(sd, x, 50, **k),
+    "resnet18_vd": lambda sd, x, **k: resnet_vd(sd, x, 18, **k),
 }
 
 

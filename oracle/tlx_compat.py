@@ -48,6 +48,8 @@ class _TrackedList(list):
             self.append(it)
 
     def append(self, item):
+        if type(item) is list and item and all(isinstance(v, torch.nn.Module) for v in item):
+            item = torch.nn.ModuleList(item)      # list of lists (segmentation/backbones/resnet_vd.py:287): <attr>.<i>.<j>
         super().append(item)
         if isinstance(item, torch.nn.Module):
             owner = self._owner
@@ -213,6 +215,24 @@ class MaxPool2d(Module):
         return F.max_pool2d(x, self.kernel_size, self.stride, self.padding)
 
 
+class AvgPool2d(Module):
+    """``padding="SAME"`` pads only where the windows do not tile the map (ceil mode, zeros excluded from the count is what
+    tensorlayerx's torch backend does [recalled]); the hot path only meets maps the 2x2 / stride-2 windows tile exactly."""
+
+    def __init__(self, kernel_size=(2, 2), stride=(2, 2), padding="SAME", data_format="channels_last", name=None):
+        super().__init__(name)
+        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+
+    def forward(self, x):
+        k = self.kernel_size if isinstance(self.kernel_size, int) else self.kernel_size[0]
+        st = self.stride if isinstance(self.stride, int) else self.stride[0]
+        if isinstance(self.padding, str):
+            if (x.shape[2] - k) % st or (x.shape[3] - k) % st:
+                raise NotImplementedError("AvgPool2d(padding='SAME') on a map the windows do not tile")
+            return F.avg_pool2d(x, k, st, 0)
+        return F.avg_pool2d(x, k, st, self.padding)
+
+
 class AdaptiveAvgPool2d(Module):
     def __init__(self, output_size, data_format="channels_last", name=None):
         super().__init__(name)
@@ -302,8 +322,14 @@ def _build_modules():
                  "random_normal", "he_normal"):
         setattr(init, name, _Init)
     for cls in (Module, Sequential, GroupConv2d, Conv2d, BatchNorm, BatchNorm2d, ReLU, ReLU6, LeakyReLU, Dropout,
-                MaxPool2d, AdaptiveAvgPool2d, Linear):
+                MaxPool2d, AvgPool2d, AdaptiveAvgPool2d, Linear):
         setattr(nn, cls.__name__, cls)
+    # nn.layers.activation / nn.layer.activation: segmentation/layers/activation.py:24-35 looks activations up by name
+    act_ns = types.ModuleType("tensorlayerx.nn.layers.activation")
+    act_ns.ReLU, act_ns.ReLU6, act_ns.LeakyReLU = ReLU, ReLU6, LeakyReLU
+    layers_ns = types.ModuleType("tensorlayerx.nn.layers")
+    layers_ns.activation = act_ns
+    nn.layers = nn.layer = layers_ns
     nn.BatchNorm2d = BatchNorm
     nn.BatchNorm2D = BatchNorm
     nn.Conv2d = GroupConv2d

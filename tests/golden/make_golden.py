@@ -41,6 +41,8 @@ CASES = {
     "darknet53_det": (1, 64),
     "yolov3_darknet53": (1, 64),          # backbone + YOLOv3FPN + head output convs: 9 maps
     "mobilenet_v1_det": (2, 96),
+    "resnet50_vd": (1, 128),              # segmentation backbone: AvgPool2d shortcut, dilation 2 / 4; four stage outputs
+    "resnet18_vd": (2, 96),
 }
 MANIFEST_ONLY = ["resnet34", "resnet101", "wide_resnet50_2", "resnext50_64x4d"]
 

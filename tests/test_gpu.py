@@ -925,3 +925,23 @@ def test_conv_to_1x1_chain_kernel(cin, mid, cout, hw, stride, n, res):
     assert float((unfused - y).abs().max()) <= tol
     # same operands, same bf16 intermediate, fp32 accumulation in another order: within one bf16 ulp of each other
     assert float((fused - unfused).abs().max()) <= 2.0 ** -7 * max(1.0, float(y.abs().max()))
+
+
+@pytest.mark.parametrize("name,n,size", [("resnet50_vd", 1, 128), ("resnet18_vd", 2, 96)])
+def test_resnet_vd_segmentation_backbone_vs_reference_golden(name, n, size):
+    """segmentation/backbones/resnet_vd.py:172-326: 3x3 stem convs, AvgPool2d(2, 2) in front of the strided shortcut conv,
+    dilation 2 / 4 in the last two stages (output stride 8), four stage outputs."""
+    outs, refs = _model_case(name, n, size, "bf16", golden=True)
+    assert len(outs) == 4 and outs[2].shape[2:] == outs[1].shape[2:] == outs[3].shape[2:]      # dilated stages keep H/8
+    for o, r in zip(outs, refs):
+        rel_max, rel_rms, _ = _rel_errors(o, r)
+        assert rel_max <= 0.03 and rel_rms <= 0.01, (rel_max, rel_rms)
+    outs32, refs32 = _model_case(name, n, size, "f32")
+    for o, r in zip(outs32, refs32):
+        assert float((o - r).abs().max()) <= 1e-4 * max(1.0, float(r.abs().max()))
+    from tlxcv_b200 import models
+    m = models.REGISTRY[name]().cuda().set_eval()
+    m(torch.randn(1, 3, 64, 64, device="cuda"))
+    plan = next(iter(m.__dict__["_b200_plans"].values()))[0]
+    kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
+    assert "avgpool_nhwc" in kernels

@@ -341,6 +341,34 @@ __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
   Vec8<T>::store(dst + idx * 8, m);
 }
 
+// AvgPool2d(k, stride) without padding (the 2x2 / stride-2 pool in front of the shortcut conv of a ResNet_vd block,
+// segmentation/backbones/resnet_vd.py:25-27,45-46): fp32 sum of the window in (r, s) order, times 1 / k^2, one rounding
+template <typename T>
+__global__ void avgpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C8, int P, int Q, int k,
+                                    int stride, size_t total) {
+  pdl_wait();
+  const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int c8 = static_cast<int>(idx % C8);
+  size_t t = idx / C8;
+  const int q = static_cast<int>(t % Q);
+  t /= Q;
+  const int pp = static_cast<int>(t % P);
+  const size_t n = t / P;
+  float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int r = 0; r < k; ++r)
+    for (int s2 = 0; s2 < k; ++s2) {
+      float v[8];
+      Vec8<T>::load(src + ((n * H + pp * stride + r) * W + q * stride + s2) * static_cast<size_t>(C8) * 8 + c8 * 8, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) m[i] += v[i];
+    }
+  const float inv = 1.0f / static_cast<float>(k * k);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] *= inv;
+  Vec8<T>::store(dst + idx * 8, m);
+}
+
 // global average pool: block per image, blockDim = (8-channel groups, kGapSlices pixel slices).  Each thread sums its
 // slice of the pixels in pixel order (fp32), the slices are then added in slice order through shared memory: four times
 // the loads in flight of a thread-per-group kernel, which was latency-bound (49 dependent-issue loads per thread).
@@ -837,6 +865,17 @@ cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C,
     TLXCV_LAUNCH((maxpool_nhwc_kernel<__nv_bfloat16, 3>), blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   else
     TLXCV_LAUNCH((maxpool_nhwc_kernel<__nv_bfloat16, 0>), blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
+  return cudaGetLastError();
+}
+
+cudaError_t avgpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int is_f32,
+                         cudaStream_t st) {
+  if (C % 8 || (P - 1) * stride + k > H || (Q - 1) * stride + k > W) return cudaErrorInvalidValue;
+  const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
+  if (is_f32)
+    TLXCV_LAUNCH(avgpool_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, total);
+  else
+    TLXCV_LAUNCH(avgpool_nhwc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, total);
   return cudaGetLastError();
 }
 

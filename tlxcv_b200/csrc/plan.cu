@@ -32,7 +32,7 @@ struct TensorRt {
 };
 
 enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
-                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat, kImplSoftmax, kImplSoftmaxCe };
+                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat, kImplSoftmax, kImplSoftmaxCe, kImplAvgpool };
 
 struct OpRt {
   tlxcv_op_desc d;
@@ -588,6 +588,9 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
     case kImplMaxpool:
       TLX_CUDA(ctx, maxpool_nhwc(pin, pout, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, d.r, d.stride, d.pad, is_f32, st));
       break;
+    case kImplAvgpool:
+      TLX_CUDA(ctx, avgpool_nhwc(pin, pout, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, d.r, d.stride, is_f32, st));
+      break;
     case kImplGap:
       TLX_CUDA(ctx, gap_nhwc(pin, pout, in.d.n, in.d.h * in.d.w, in.d.c, is_f32, st));
       break;
@@ -1054,6 +1057,14 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
           return fail(ctx, TLXCV_ERR_INVALID, "op %d: maxpool output shape mismatch", i);
         op.impl = kImplMaxpool;
         set_info(op, "maxpool_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      case TLXCV_OP_AVGPOOL:
+        if (d.r != d.s || d.pad != 0 || d.r < 1 || d.stride < 1)
+          return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: average pooling needs a square window without padding", i);
+        if (o.d.h != (in.d.h - d.r) / d.stride + 1 || o.d.w != (in.d.w - d.r) / d.stride + 1 || o.d.c != in.d.c || in.cs != in.d.c)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: avgpool output shape mismatch", i);
+        op.impl = kImplAvgpool;
+        set_info(op, "avgpool_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_GAP:
         if (o.d.h != 1 || o.d.w != 1 || o.d.c != in.d.c) return fail(ctx, TLXCV_ERR_INVALID, "op %d: gap output shape mismatch", i);

@@ -198,6 +198,15 @@ class Graph:
         q = (w + 2 * pw - kw) // sw + 1
         return self._emit("maxpool", [x], (n, c, p, q), dict(k=(kh, kw), stride=(sh, sw), pad=(ph, pw)))
 
+    def avgpool(self, x, k, stride, pad) -> SymTensor:
+        n, c, h, w = _nchw(x, "AvgPool2d")
+        (kh, kw), (sh, sw), (ph, pw) = k, stride, pad
+        if (ph, pw) != (0, 0) or kh != kw or sh != sw:
+            raise NotImplementedError("AvgPool2d: only square windows without padding are on the hot path")
+        if (h - kh) % sh or (w - kw) % sw:
+            raise NotImplementedError(f"AvgPool2d({kh}, {sh}) on a {h}x{w} map: windows must tile the map exactly")
+        return self._emit("avgpool", [x], (n, c, (h - kh) // sh + 1, (w - kw) // sw + 1), dict(k=(kh, kw), stride=(sh, sw)))
+
     def gap(self, x) -> SymTensor:
         n, c, h, w = _nchw(x, "AdaptiveAvgPool2d")
         return self._emit("gap", [x], (n, c, 1, 1))

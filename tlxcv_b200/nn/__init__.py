@@ -23,7 +23,7 @@ from .initializers import _resolve
 
 __all__ = [
     "Module", "Layer", "Sequential", "GroupConv2d", "Conv2d", "BatchNorm", "BatchNorm2d", "BatchNorm2D", "ReLU",
-    "ReLU6", "LeakyReLU", "Dropout", "MaxPool2d", "AdaptiveAvgPool2d", "Linear", "initializers",
+    "ReLU6", "LeakyReLU", "Dropout", "MaxPool2d", "AvgPool2d", "AdaptiveAvgPool2d", "Linear", "initializers", "layers", "layer",
 ]
 
 _ACT_NAMES = {"relu": ("relu", 0.0), "relu6": ("relu6", 0.0), "leaky_relu": ("leaky", 0.2), "lrelu": ("leaky", 0.2)}
@@ -45,6 +45,10 @@ class _LayerList(list):
             self.append(it)
 
     def append(self, item):
+        if type(item) is list and item and all(isinstance(v, torch.nn.Module) for v in item):
+            # a list of lists (segmentation/backbones/resnet_vd.py:287 `self.stage_list.append(block_list)`): the inner list
+            # registers as `<attr>.<i>.<j>`
+            item = _NestedLayers(item)
         super().append(item)
         if isinstance(item, torch.nn.Module):
             mods = self._owner._modules
@@ -56,6 +60,10 @@ class _LayerList(list):
     def extend(self, items):
         for it in items:
             self.append(it)
+
+
+class _NestedLayers(torch.nn.ModuleList):
+    """Inner list of a list of lists of layers: iterates / indexes like the Python list it replaces."""
 
 
 class Module(torch.nn.Module):
@@ -392,6 +400,25 @@ class MaxPool2d(Module):
         return _g.active().maxpool(_sym(x, "MaxPool2d"), self.kernel_size, self.stride, self.padding)
 
 
+class AvgPool2d(Module):
+    """``nn.AvgPool2d(kernel_size, stride, padding)``; ``padding="SAME"`` is accepted where it adds nothing (windows that tile
+    the map exactly: the 2x2 / stride-2 pool of ResNet_vd's shortcut on even maps, segmentation/backbones/resnet_vd.py:25-27)."""
+
+    def __init__(self, kernel_size=(2, 2), stride=(2, 2), padding="SAME", data_format="channels_first", name=None):
+        super().__init__(name)
+        _check_format(data_format)
+        self.kernel_size = _pair(kernel_size, "kernel_size")
+        self.stride = _pair(stride, "stride")
+        if isinstance(padding, str):
+            if padding.upper() not in ("SAME", "VALID"):
+                raise NotImplementedError(f"AvgPool2d padding {padding!r}")
+            padding = 0          # SAME on a map the windows tile exactly == no padding (checked when traced)
+        self.padding = _pair(padding, "padding")
+
+    def forward(self, x):
+        return _g.active().avgpool(_sym(x, "AvgPool2d"), self.kernel_size, self.stride, self.padding)
+
+
 class AdaptiveAvgPool2d(Module):
     def __init__(self, output_size, data_format="channels_first", name=None):
         super().__init__(name)
@@ -428,3 +455,17 @@ class Linear(Module):
         if self._tlx_act is not None:
             raise NotImplementedError("Linear(act=...) is not on the hot path")
         return _g.active().linear(_sym(x, "Linear"), self)
+
+
+class _ActivationNamespace:
+    """``tensorlayerx.nn.layers.activation`` / ``nn.layer.activation`` as far as the reference reaches into it
+    (segmentation/layers/activation.py:24-35 looks activations up by lower-cased class name and instantiates them)."""
+    ReLU, ReLU6, LeakyReLU = ReLU, ReLU6, LeakyReLU
+
+
+class _LayersNamespace:
+    activation = _ActivationNamespace
+
+
+layers = _LayersNamespace
+layer = _LayersNamespace

@@ -23,7 +23,7 @@ from . import graph as _g
 
 # op kinds / activations / dtypes: keep in sync with include/tlxcv_b200.h
 (OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW, OP_IMPORT_U8,
- OP_UPSAMPLE_CONCAT, OP_SOFTMAX, OP_SOFTMAX_CE) = range(12)
+ OP_UPSAMPLE_CONCAT, OP_SOFTMAX, OP_SOFTMAX_CE, OP_AVGPOOL) = range(13)
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY = range(4)
 DT_U8 = 4
 DT_F32, DT_BF16, DT_I64, DT_ACT = 0, 1, 2, 3          # DT_ACT: bf16 in the default mode, f32 in validation mode
@@ -31,7 +31,7 @@ ROLE_INTERNAL, ROLE_INPUT, ROLE_OUTPUT = 0, 1, 2
 
 _ACT = {None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6, "leaky": ACT_LEAKY}
 OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw", "import_u8_nhwc",
-            "upsample_concat", "softmax", "softmax_ce"]
+            "upsample_concat", "softmax", "softmax_ce", "avgpool"]
 
 
 @dataclass
@@ -271,6 +271,11 @@ def lower(graph: _g.Graph) -> PlanSpec:
             spec.ops.append(OpSpec(OP_MAXPOOL, ins[0], out, r=a["k"][0], s=a["k"][1],
                                    stride=_square(a["stride"], "stride", nd.path),
                                    pad=_square(a["pad"], "padding", nd.path), path=nd.path))
+        elif nd.op == "avgpool":
+            a = nd.attrs
+            out = new_tensor(graph.shapes[nd.out], DT_ACT)
+            spec.ops.append(OpSpec(OP_AVGPOOL, ins[0], out, r=a["k"][0], s=a["k"][1], stride=a["stride"][0], pad=0,
+                                   path=nd.path))
         elif nd.op == "gap":
             out = new_tensor(graph.shapes[nd.out], DT_ACT)
             spec.ops.append(OpSpec(OP_GAP, ins[0], out, path=nd.path))

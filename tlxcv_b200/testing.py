@@ -31,6 +31,8 @@ _DAMP = {
     "mobilenet_v2": [r"features\.1\.conv\.2\.gamma$", r"features\.\d+\.conv\.3\.gamma$"],
     "darknet53_cls": [r"_basic_block_\d+\._conv2\._bn\.gamma$"],
     "darknet53_det": [r"\.conv2\.batch_norm\.gamma$"],
+    "resnet_vd_bottleneck": [r"\.conv2\.batch_norm\.gamma$"],
+    "resnet_vd_basic": [r"stage_list\.\d+\.\d+\.conv1\.batch_norm\.gamma$"],
 }
 
 # model name -> (damp family, FC gain chosen so that logits std is ~0.25-0.3 on randn images)
@@ -51,6 +53,8 @@ RECIPES = {
     "darknet53_det": ("darknet53_det", 1.0),
     "yolov3_darknet53": ("darknet53_det", 1.0),
     "mobilenet_v1_det": ("mobilenet_v1", 1.0),
+    "resnet50_vd": ("resnet_vd_bottleneck", 1.0),
+    "resnet18_vd": ("resnet_vd_basic", 1.0),
 }
 
 
