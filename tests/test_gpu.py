@@ -132,7 +132,13 @@ LAYERS = {
     "pair_3x3_s2_c256_leaky": (dict(n=3, cin=256, hw=19, cout=512, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col_n256_2sm"),
     "pair_3x3_c256_14x14_bs9": (dict(n=9, cin=256, hw=14, cout=256, k=3, stride=1, pad=1, act="relu"), "conv_tcgen05_im2col_n256_2sm"),
     "im2col_1x1_s2_downsample": (dict(n=2, cin=256, hw=14, cout=512, k=1, stride=2, pad=0), "conv_tcgen05_im2col"),
-    "im2col_3x3_c32_leaky": (dict(n=2, cin=32, hw=20, cout=64, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col"),
+    "pixelpairs_3x3_s2_c32_leaky": (dict(n=2, cin=32, hw=20, cout=64, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col_n64_pixelpairs"),
+    "pixelpairs_w38_residual": (dict(n=3, cin=32, hw=38, cout=64, k=3, stride=2, pad=1, act="leaky", res=True), "conv_tcgen05_im2col_n64_pixelpairs"),
+    "pixelpairs_w304_rows_wrap": (dict(n=1, cin=32, hw=304, cout=64, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_im2col_n64_pixelpairs"),
+    "pixelpairs_cout_128_two_n_tiles": (dict(n=2, cin=32, hw=18, cout=128, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_im2col_n64_pixelpairs"),
+    "im2col_kb32_odd_75_residual": (dict(n=3, cin=32, hw=75, cout=64, k=3, stride=2, pad=1, act="leaky", res=True), "conv_tcgen05_im2col_n64_kb32"),
+    "im2col_kb32_cout_32_s1_5x5": (dict(n=2, cin=32, hw=17, cout=32, k=5, stride=1, pad=2, act="relu"), "conv_tcgen05_im2col_n64_kb32"),
+    "im2col_c32_cout_128_odd_19_keeps_64_wide_k_blocks": (dict(n=2, cin=32, hw=19, cout=128, k=3, stride=2, pad=1, act="relu"), "conv_tcgen05_im2col_n"),
     "im2col_leaky_then_residual": (dict(n=2, cin=64, hw=10, cout=128, k=3, stride=1, pad=1, act="leaky", res=True),
                                    "conv_tcgen05_im2col"),
     "im2col_odd_size_19": (dict(n=1, cin=64, hw=19, cout=128, k=3, stride=2, pad=1, act="leaky"), "conv_tcgen05_im2col"),

@@ -44,11 +44,14 @@ constexpr int kMaxStages = 8;
 constexpr int kThreadsBase = (2 + kEpiWarps) * 32;                // 320
 constexpr int kThreadsGather = kThreadsBase + kGatherWarps * 32;  // 576
 
-template <int BLOCK_N>
+// KB = channels per K block: 64 (128-byte rows, SWIZZLE_128B), or 32 (64-byte rows, SWIZZLE_64B) for layers with 32 input
+// channels, whose 64-wide K blocks would be half zero padding (DarkNet's 32 -> 64 3x3 / stride-2 conv at 608x608)
+template <int BLOCK_N, int KB = kBlockK>
 struct Cfg {
-  static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-  static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStageBytes2 = kABytes + kBBytes / 2;  // cta_group::2: each CTA of the pair stages half of B
+  static constexpr int kAB = kBlockM * KB * 2;
+  static constexpr int kBBytes = BLOCK_N * KB * 2;
+  static constexpr int kStageBytes = kAB + kBBytes;
+  static constexpr int kStageBytes2 = kAB + kBBytes / 2;  // cta_group::2: each CTA of the pair stages half of B
   // smem layout: [stages x (A | B)] [8 warps x ring x 2 KB] [scale cache] [barriers]; the ring depth
   // and therefore the stage count are chosen per layer (deep ring for residual / HBM-bound layers,
   // more operand stages for MMA-bound ones)
@@ -575,13 +578,15 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
 // issues 256x256x16 MMAs that read both CTAs' shared memory and write both CTAs' TMEM, every CTA drains its own 128
 // accumulator rows.  Per CTA and K block that is 16 KB + 16 KB from L2 instead of 16 KB + 32 KB: the MMA-bound
 // layers are limited by exactly that L2 -> SM operand traffic.
-template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
+template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false, int KB = kBlockK>
 __global__ void __launch_bounds__(MODE == kModeGatherC4 ? kThreadsGather : kThreadsBase, 1)
 conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_constant__ CUtensorMap tmapB,
                     const __grid_constant__ CUtensorMap tmapOut, const __grid_constant__ CUtensorMap tmapRes,
                     const __grid_constant__ CUtensorMap tmapA2, const __grid_constant__ CUtensorMap tmapB2,
                     const ConvKernelParams p) {
-  using C = Cfg<BLOCK_N>;
+  using C = Cfg<BLOCK_N, KB>;
+  static_assert(KB == kBlockK || (KB == 32 && MODE == kModeIm2col && !DUAL && !TWO), "32-channel K blocks: plain im2col tiles");
+  constexpr int kAB = C::kAB;  // bytes of one A tile
   static_assert(!DUAL || (BLOCK_N == 128 && MODE == kModeTiled), "dual accumulators: 128-wide tiles over a tiled first operand");
   static_assert(!TWO || ((BLOCK_N == 256 || BLOCK_N == 128) && !DUAL && MODE != kModeGatherC4), "CTA pairs: 128/256-wide plain tiles");
   constexpr int kAccCols = DUAL ? 2 * BLOCK_N : BLOCK_N;  // TMEM columns per accumulator buffer
@@ -690,16 +695,16 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             }
             if (rank == 0) mbar_arrive_expect_tx(bar, 2 * kStageB);
             if (MODE == kModeTiled) {
-              tma_load_2d_2sm(a_dst, &tmapA, lbar, kb * kBlockK, m0);
+              tma_load_2d_2sm(a_dst, &tmapA, lbar, kb * KB, m0);
             } else {
-              tma_load_im2col_4d_2sm(a_dst, &tmapA, lbar, c_base + cb * kBlockK, base_w, base_h, img,
+              tma_load_im2col_4d_2sm(a_dst, &tmapA, lbar, c_base + cb * KB, base_w, base_h, img,
                                      static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
               if (++cb == p.kb_per_tap) {
                 cb = 0;
                 if (++sx == p.S) sx = 0, ++r;
               }
             }
-            tma_load_2d_2sm(a_dst + kABytes, &tmapB, lbar, kb * kBlockK, n0 + static_cast<int>(rank) * (BLOCK_N / 2));
+            tma_load_2d_2sm(a_dst + kAB, &tmapB, lbar, kb * KB, n0 + static_cast<int>(rank) * (BLOCK_N / 2));
             ps.advance(n_stages);
             continue;
           }
@@ -713,24 +718,29 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             // second GEMM: 1x1 filter, so the K block is just a 64-channel slice of the (strided) input pixels
             const int kb2 = kb - p.num_kb1;
             if (p.a2_im2col)
-              tma_load_im2col_4d(a_dst, &tmapA2, bar, kb2 * kBlockK, base_w, base_h, img, 0, 0);
+              tma_load_im2col_4d(a_dst, &tmapA2, bar, kb2 * KB, base_w, base_h, img, 0, 0);
             else
-              tma_load_2d(a_dst, &tmapA2, bar, kb2 * kBlockK, m0);
-            tma_load_2d(a_dst + kABytes, &tmapB2, bar, kb2 * kBlockK, n0);
+              tma_load_2d(a_dst, &tmapA2, bar, kb2 * KB, m0);
+            tma_load_2d(a_dst + kAB, &tmapB2, bar, kb2 * KB, n0);
             ps.advance(n_stages);
             continue;
           }
           if (MODE == kModeTiled) {
-            tma_load_2d(a_dst, &tmapA, bar, kb * kBlockK, m0);
+            tma_load_2d(a_dst, &tmapA, bar, kb * KB, m0);
+          } else if (MODE == kModeIm2col && KB == kBlockK && p.pair_taps != 0) {
+            // pixel-pair layout: K block -> (even / odd input rows map, pair offset, row offset); base_w / base_h are in pair space
+            const uint32_t e = p.pair_taps >> (4 * kb);
+            tma_load_im2col_4d(a_dst, (e & 1) ? &tmapA2 : &tmapA, bar, 0, base_w, base_h, img, static_cast<uint16_t>((e >> 1) & 1),
+                               static_cast<uint16_t>((e >> 2) & 1));
           } else if (MODE == kModeIm2col) {
-            tma_load_im2col_4d(a_dst, &tmapA, bar, c_base + cb * kBlockK, base_w, base_h, img,
+            tma_load_im2col_4d(a_dst, &tmapA, bar, c_base + cb * KB, base_w, base_h, img,
                                static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
             if (++cb == p.kb_per_tap) {
               cb = 0;
               if (++sx == p.S) sx = 0, ++r;
             }
           }
-          tma_load_2d(a_dst + kABytes, &tmapB, bar, kb * kBlockK, n0);
+          tma_load_2d(a_dst + kAB, &tmapB, bar, kb * KB, n0);
           ps.advance(n_stages);
         }
         trace_c(p.trace, 0, tr);  // [2k+1] all loads of the tile issued
@@ -744,7 +754,8 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
     if (rank == 0) {  // in a CTA pair only the leader issues
       constexpr uint32_t idesc = make_idesc_bf16(TWO ? 2 * kBlockM : kBlockM, BLOCK_N);
       // make_kmajor_sw128_desc split in words: high = SBO 1024 B | version 1 | SWIZZLE_128B, low = address >> 4 | LBO 1
-      constexpr uint32_t desc_hi = (1024u >> 4) | (1u << 14) | (2u << 29);
+      // (64-byte rows: 8-row atoms of 512 B, SWIZZLE_64B)
+      constexpr uint32_t desc_hi = KB == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
       const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);  // descriptor low word of stage 0
       const bool tracer1 = lane == 0 && p.trace != nullptr;
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
@@ -783,10 +794,10 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
               const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
               const int kbl = second ? kk - num_kb1 : kk;  // first K block of an accumulator overwrites it
               const uint32_t a_lo = smem_lo + st * (kStageB >> 4);
-              const uint32_t b_lo = a_lo + (kABytes >> 4);
+              const uint32_t b_lo = a_lo + (kAB >> 4);
               if (!no_mma) {
 #pragma unroll
-                for (int k = 0; k < kBlockK / 16; ++k) {
+                for (int k = 0; k < KB / 16; ++k) {
                   // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
                   if (k == 0)
                     umma_bf16_lohi<TWO>(tmem_d, a_lo, b_lo, desc_hi, idesc, kbl != 0);
@@ -1356,16 +1367,20 @@ std::string encode_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
   return "";
 }
 
+// row_bytes / image_bytes: byte strides of the H and N dimensions (0 = dense NHWC); pad_hi: padding on the high side (-1 = pad)
 std::string encode_im2col(CUtensorMap* map, const void* base, int N, int H, int W, int C, int R, int S, int stride,
-                          int pad, int dil) {
+                          int pad, int dil, int kb = kBlockK, uint64_t row_bytes = 0, uint64_t image_bytes = 0, int pad_hi = -1) {
+  if (pad_hi < 0) pad_hi = pad;
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
-  // bounding box of base pixels: lower = -pad, upper = pad - (filter-1)*dilation  (W, H order)
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, row_bytes ? row_bytes : (cuuint64_t)W * C * 2,
+                           image_bytes ? image_bytes : (cuuint64_t)H * W * C * 2};
+  // bounding box of base pixels: lower = -pad, upper = pad_hi - (filter-1)*dilation  (W, H order)
   int lower[2] = {-pad, -pad};
-  int upper[2] = {pad - (S - 1) * dil, pad - (R - 1) * dil};
+  int upper[2] = {pad_hi - (S - 1) * dil, pad_hi - (R - 1) * dil};
   cuuint32_t estr[4] = {1, (cuuint32_t)stride, (cuuint32_t)stride, 1};
   CUresult r = g_encode_im2col(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, lower,
-                               upper, kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               upper, kb, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     char buf[256];
@@ -1401,7 +1416,7 @@ cudaError_t launch_pair(void (*kernel)(KArgs...), int grid, int block, size_t sm
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
-template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
+template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false, int KB = kBlockK>
 cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
   // debugging: dump CTA 0's timeline of conv launch number TLXCV_DEBUG_TRACE_CONV_INDEX (default: every launch, so the
   // file holds the last one)
@@ -1416,10 +1431,10 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
     ConvKernelParams p = L.p;
     p.trace = dbuf;
     if (TWO)
-      launch_pair(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut, L.tmapRes,
+      launch_pair(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO, KB>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut, L.tmapRes,
                   L.tmapA2, L.tmapB2, p);
     else
-      conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.tmapA2, L.tmapB2, p);
+      conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO, KB><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapOut, L.tmapRes, L.tmapA2, L.tmapB2, p);
     cudaStreamSynchronize(st);
     std::vector<unsigned long long> h(3 * kTraceLenC);
     cudaMemcpy(h.data(), dbuf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
@@ -1430,24 +1445,26 @@ cudaError_t launch_t(const TcConvLaunch& L, cudaStream_t st) {
     return cudaGetLastError();
   }
   if (TWO)
-    return launch_pair(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
+    return launch_pair(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO, KB>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
                        L.tmapRes, L.tmapA2, L.tmapB2, L.p);
-  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
+  return launch_pdl(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO, KB>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapOut,
                     L.tmapRes, L.tmapA2, L.tmapB2, L.p);
 }
 
-template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false>
+template <int BLOCK_N, int MODE, bool DUAL = false, bool TWO = false, int KB = kBlockK>
 cudaError_t set_attr_t() {
-  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  return cudaFuncSetAttribute(conv_tcgen05_kernel<BLOCK_N, MODE, DUAL, TWO, KB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                               kSmemLimit);
 }
 
-int smem_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
+int smem_for(int block_n, int ring, int sc_bufs, int ew, bool two = false, int kb = kBlockK) {
+  if (kb == 32) return Cfg<64, 32>::smem_bytes(ring, sc_bufs, ew);
   if (two) return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs, ew, true) : Cfg<128>::smem_bytes(ring, sc_bufs, ew, true);
   return block_n == 256 ? Cfg<256>::smem_bytes(ring, sc_bufs, ew)
                         : (block_n == 128 ? Cfg<128>::smem_bytes(ring, sc_bufs, ew) : Cfg<64>::smem_bytes(ring, sc_bufs, ew));
 }
-int stages_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
+int stages_for(int block_n, int ring, int sc_bufs, int ew, bool two = false, int kb = kBlockK) {
+  if (kb == 32) return Cfg<64, 32>::stages_for(ring, sc_bufs, ew);
   if (two) return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs, ew, true) : Cfg<128>::stages_for(ring, sc_bufs, ew, true);
   return block_n == 256 ? Cfg<256>::stages_for(ring, sc_bufs, ew)
                         : (block_n == 128 ? Cfg<128>::stages_for(ring, sc_bufs, ew) : Cfg<64>::stages_for(ring, sc_bufs, ew));
@@ -1459,7 +1476,7 @@ int stages_for(int block_n, int ring, int sc_bufs, int ew, bool two = false) {
 // faster: ResNet-50 bs256 3.67 ms against 3.51 ms - the per-SM epilogue rate is set by shared-memory traffic (staging
 // stores, TMA store reads, scale/shift broadcasts next to the MMA operand reads) and the per-chunk proxy fence, not by
 // the number of warps issuing.
-void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_bf16, bool two = false) {
+void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_bf16, bool two = false, int kb = kBlockK) {
   static const int force = tuning_env("TLXCV_DEBUG_EPI_WARPS") ? atoi(tuning_env("TLXCV_DEBUG_EPI_WARPS")) : 0;
   const bool light = p.num_kb <= 8;
   p.epi_warps = 8;
@@ -1470,10 +1487,10 @@ void choose_epilogue(ConvKernelParams& p, int block_n, bool residual, bool out_b
   if (!out_bf16) p.ring = 2;
   // scale/shift: one smem buffer filled once (single N tile); two buffers refreshed per tile by the epilogue
   // warps (several N tiles) unless that second buffer would cost an operand stage: then read through __ldg
-  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps, two) == stages_for(block_n, p.ring, 1, p.epi_warps, two)) ? 2 : 1;
+  p.sc_bufs = (p.n_tiles > 1 && stages_for(block_n, p.ring, 2, p.epi_warps, two, kb) == stages_for(block_n, p.ring, 1, p.epi_warps, two, kb)) ? 2 : 1;
   if (const char* e = tuning_env("TLXCV_DEBUG_SC_BUFS")) p.sc_bufs = atoi(e) == 2 && p.n_tiles > 1 ? 2 : 1;  // A/B timing only
   if (const char* e = tuning_env("TLXCV_DEBUG_RING")) p.ring = (atoi(e) == 4 && out_bf16) ? 4 : 2;  // A/B timing only
-  p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
+  p.stages = stages_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two, kb);
   if (const char* e = tuning_env("TLXCV_DEBUG_STAGES")) p.stages = std::max(2, std::min(p.stages, atoi(e)));  // A/B timing only
 }
 
@@ -1485,7 +1502,17 @@ int tc_conv_mode(int Cin, int R, int S, int stride, int pad, int groups) {
   return kModeIm2col;
 }
 
-int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode) {
+int tc_conv_layout(int Cin, int Cout, int R, int S, int stride, int pad, int dil, int groups, int H, int W) {
+  if (tc_conv_mode(Cin, R, S, stride, pad, groups) != kModeIm2col || groups != 1 || Cin != 32) return kLayoutPlain;
+  if (R == 3 && S == 3 && stride == 2 && pad == 1 && dil == 1 && H % 2 == 0 && W % 2 == 0 && !tuning_env("TLXCV_NO_PIXEL_PAIRS"))
+    return kLayoutPixelPairs;
+  if (Cout <= 64 && !tuning_env("TLXCV_NO_KB32")) return kLayoutKb32;
+  return kLayoutPlain;
+}
+
+int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode, int layout) {
+  if (layout == kLayoutKb32) return R * S * 32;
+  if (layout == kLayoutPixelPairs) return 6 * kBlockK;
   if (mode == kModeGatherC4) {
     const int KR = (S * 4 <= 16) ? 16 : 32;
     const int r_per_kb = kBlockK / KR;
@@ -1508,6 +1535,7 @@ cudaError_t tc_conv_set_attributes() {
   if ((e = set_attr_t<256, kModeIm2col, false, true>()) != cudaSuccess) return e;
   if ((e = set_attr_t<128, kModeTiled, false, true>()) != cudaSuccess) return e;
   if ((e = set_attr_t<128, kModeIm2col, false, true>()) != cudaSuccess) return e;
+  if ((e = set_attr_t<64, kModeIm2col, false, false, 32>()) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_chain_kernel<64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_chain_kernel<64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
   if ((e = cudaFuncSetAttribute(conv_chain_kernel<128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit)) != cudaSuccess) return e;
@@ -1536,6 +1564,8 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   if (residual_bf16 != nullptr && Cout_storage != Cout) return "conv: a residual needs an unpadded output";
 
   int block_n;
+  int kb = kBlockK;  // channels per K block
+  int layout = kLayoutPlain;
   if (mode == kModeGatherC4) {
     if (S * 4 > 32) return "stem conv: filter width > 8 is not supported";
     if (Cin_storage != 4) return "stem conv: input must be stored as NHWC4";
@@ -1556,8 +1586,18 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
     block_n = 64;
   } else {
     if (Cin % 8) return "conv: C_in must be a multiple of 8 on the tensor-core path";
-    p.kb_per_tap = (Cin + kBlockK - 1) / kBlockK;
+    layout = tc_conv_layout(Cin, Cout, R, S, stride, pad, dil, groups, H, W);
+    kb = layout == kLayoutKb32 ? 32 : kBlockK;
+    p.kb_per_tap = (Cin + kb - 1) / kb;
     p.num_kb = R * S * p.kb_per_tap;
+    if (layout == kLayoutPixelPairs) {
+      // K block -> {valid | row offset | pair offset | odd-row map}: filter rows 1, 2, 0 read input rows 2*oy (even map, row oy),
+      // 2*oy + 1 (odd map, row oy) and 2*oy - 1 (odd map, row oy - 1); bases are (oy - 1, ox - 1) in pair space
+      p.num_kb = 6, p.kb_per_tap = 1;
+      static const unsigned taps[6] = {8 | 4 | 2 | 0, 8 | 4 | 2 | 1, 8 | 0 | 2 | 1, 8 | 4 | 0 | 0, 8 | 4 | 0 | 1, 8 | 0 | 0 | 1};
+      for (int j = 0; j < 6; ++j) p.pair_taps |= taps[j] << (4 * j);
+      p.stride = 1, p.pad = 1;  // the producer's base coordinates: pair space, stride 1, one pair / row of padding on the low side
+    }
     // tile width: minimise (waves x per-tile MMA time); N=64 tiles are shared-memory-bandwidth limited
     const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
     double best = 1e30;
@@ -1576,7 +1616,9 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
     if (!(groups > 1 && force_block_n != 64) && !(mode == kModeGatherC4 && force_block_n == 256))
       block_n = force_block_n;
   }
-  if (Ktot != p.num_kb * kBlockK) return "conv: packed weight K does not match the kernel's K blocking";
+  if (kb == 32 && block_n != 64) return "conv: 32-channel K blocks need a 64-wide tile";
+  if (Ktot != p.num_kb * kb) return "conv: packed weight K does not match the kernel's K blocking";
+  L.kblock = kb;
   p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
   p.n_tiles = (Cout + block_n - 1) / block_n;
   L.mode = mode;
@@ -1589,26 +1631,37 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // rather than by the epilogue; TLXCV_DEBUG_2SM=0/1 forces it off / on where legal
   // (measured on B200, bs256: 14x14 maps 1024->256 35.8 -> 33.8 us, 512->1024 58.4 -> 54.3 us; 7x7 maps with their 98
   //  M tiles lose 3-5 %: pairs halve the number of schedulable units)
-  const bool pairable = (block_n == 256 || block_n == 128) && groups == 1 && mode != kModeGatherC4 && out_bf16 != nullptr;
+  const bool pairable = (block_n == 256 || block_n == 128) && groups == 1 && mode != kModeGatherC4 && out_bf16 != nullptr &&
+                        layout == kLayoutPlain;
   // 128-wide pairs measured: no gain.  Few M tiles (7x7 maps: 98) pair only with a long K loop: bs256 512->512 3x3
   // 63.5 -> 57.3 us, 2048->512 33.8 -> 31.7 us, but 512->2048 + residual (8 K blocks) 38.9 -> 43.9 us.
-  bool two = pairable && block_n == 256 && ((p.num_kb >= 8 && p.m_tiles >= 256) || (p.num_kb >= 16 && p.m_tiles >= 64));
-  if (const char* e = tuning_env("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && p.m_tiles >= 2;
+  bool two = pairable && kb == kBlockK && block_n == 256 && ((p.num_kb >= 8 && p.m_tiles >= 256) || (p.num_kb >= 16 && p.m_tiles >= 64));
+  if (const char* e = tuning_env("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && kb == kBlockK && p.m_tiles >= 2;
   L.two = two ? 1 : 0;
-  choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two);
-  L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two);
+  choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two, kb);
+  L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two, kb);
   const long long tiles = two ? static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles : static_cast<long long>(p.m_tiles) * p.n_tiles;
   L.grid = two ? 2 * static_cast<int>(std::min<long long>(tiles, sm_count / 2)) : static_cast<int>(std::min<long long>(tiles, sm_count));
 
   // B: packed weights [Cout_pad][Ktot], K-major; Cout_pad is a multiple of 256 rows so any tile box is in bounds
   const int cout_pad = ((Cout + 255) / 256) * 256;
-  err = encode_2d(&L.tmapB, packed_w, Ktot, cout_pad, static_cast<uint64_t>(Ktot) * 2, kBlockK, L.two ? block_n / 2 : block_n);
+  err = encode_2d(&L.tmapB, packed_w, Ktot, cout_pad, static_cast<uint64_t>(Ktot) * 2, kb, L.two ? block_n / 2 : block_n,
+                  kb == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_128B);
   if (!err.empty()) return err;
   if (mode == kModeTiled) {
     err = encode_2d(&L.tmapA, act_in, Cin, p.M, static_cast<uint64_t>(Cin_storage) * 2, kBlockK, kBlockM);
   } else if (mode == kModeIm2col) {
     if (Cin_storage != Cin) return "conv: padded channel storage is only supported for stems";
-    err = encode_im2col(&L.tmapA, act_in, N, H, W, Cin, R, S, stride, pad, dil);
+    if (layout == kLayoutPixelPairs) {
+      // two maps over (64, W/2, H/2, N): even and odd input rows; a 2 x 2 "filter" with one pair / row of padding on the low side
+      const uint64_t row = static_cast<uint64_t>(W) * Cin * 2;
+      err = encode_im2col(&L.tmapA, act_in, N, H / 2, W / 2, 64, 2, 2, 1, 1, 1, kBlockK, 2 * row, static_cast<uint64_t>(H) * row, 0);
+      if (err.empty())
+        err = encode_im2col(&L.tmapA2, reinterpret_cast<const uint8_t*>(act_in) + row, N, H / 2, W / 2, 64, 2, 2, 1, 1, 1, kBlockK,
+                            2 * row, static_cast<uint64_t>(H) * row, 0);
+    } else {
+      err = encode_im2col(&L.tmapA, act_in, N, H, W, Cin, R, S, stride, pad, dil, kb);
+    }
   } else {
     L.tmapA = L.tmapB;  // unused
   }
@@ -1629,7 +1682,8 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   } else {
     L.tmapRes = L.tmapB;
   }
-  L.tmapA2 = L.tmapB, L.tmapB2 = L.tmapB;  // only read by dual launches
+  if (layout != kLayoutPixelPairs) L.tmapA2 = L.tmapB;  // otherwise only read by dual launches
+  L.tmapB2 = L.tmapB;
   return err;
 }
 
@@ -1751,6 +1805,7 @@ cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t st) {
   if (L.two && L.block_n == 256)
     return L.mode == kModeTiled ? launch_t<256, kModeTiled, false, true>(L, st) : launch_t<256, kModeIm2col, false, true>(L, st);
   if (L.two) return L.mode == kModeTiled ? launch_t<128, kModeTiled, false, true>(L, st) : launch_t<128, kModeIm2col, false, true>(L, st);
+  if (L.kblock == 32) return launch_t<64, kModeIm2col, false, false, 32>(L, st);
 #define TLXCV_CASE(BN, MD) \
   if (L.block_n == BN && L.mode == MD) return launch_t<BN, MD>(L, st);
   TLXCV_CASE(64, kModeTiled) TLXCV_CASE(128, kModeTiled) TLXCV_CASE(256, kModeTiled)

@@ -48,6 +48,15 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
       const int r = kb * r_per_kb + within / KR, e = within % KR;
       const int s = e / 4, c = e % 4;
       if (r < R && s < S && c < Cin) v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s];
+    } else if (mode == kModePixelPairs) {
+      // K block j < 3: filter row {1, 2, 0}[j], taps s = 1 | 2 in the two halves; j >= 3: same rows, tap s = 0 in the UPPER half
+      // (the pair to the left holds pixel 2*ox - 1 in its upper 32 channels), lower half zero
+      const int j = k / 64, half = (k % 64) / 32, c = k % 32;
+      const int r = (j % 3 == 0) ? 1 : (j % 3 == 1 ? 2 : 0);
+      if (j < 3)
+        v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + 1 + half];
+      else if (half == 1)
+        v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + 0];
     } else if (groups > 1) {
       // 64-channel block-diagonal expansion: K slot (tap, cl) holds input channel 64*(o/64)+cl
       const int tap = k / 64, cl = k % 64;
@@ -56,7 +65,7 @@ __global__ void pack_conv_weights_kernel(const float* __restrict__ w, __nv_bfloa
       const int cpg_out = Cout / groups;
       if (c < Cin && c / Cg == o / cpg_out) v = w[((static_cast<size_t>(o) * Cg + (c % Cg)) * R + r) * S + s];
     } else {
-      const int kpt = mode == kModeSlabDense ? Cin : ((Cin + 63) / 64) * 64;
+      const int kpt = mode == kModeSlabDense ? Cin : Ktot / (R * S);  // channels reserved per tap (a multiple of the K block)
       const int tap = k / kpt, c = k % kpt;
       const int r = tap / S, s = tap % S;
       if (c < Cin) v = w[((static_cast<size_t>(o) * Cin + c) * R + r) * S + s];

@@ -18,7 +18,18 @@ enum ConvMode : int {
   kModeTiled = 0,   // 1x1 stride-1: A = [M][C] plain 2-D TMA tiles
   kModeIm2col = 1,  // general RxS / stride / pad: A tiles by im2col-mode TMA from NHWC
   kModeGatherC4 = 2, // C_in <= 4 stems: producer warps gather from NHWC4 into the swizzled A tile
-  kModeSlabDense = 3 // weight packing only: K = taps x exactly C_in channels (conv3x3_slab.cu, dense layers)
+  kModeSlabDense = 3, // weight packing only: K = taps x exactly C_in channels (conv3x3_slab.cu, dense layers)
+  kModePixelPairs = 4 // weight packing only: 3x3 / stride-2 conv over 32 channels as 6 K blocks of pixel pairs (kLayoutPixelPairs)
+};
+
+// K layout of a dense im2col conv (tc_conv_layout): how the filter taps and channels map onto K blocks
+enum TcConvLayout {
+  kLayoutPlain = 0,      // K block = 64 channels of one tap (a tap with fewer channels is zero padded)
+  kLayoutKb32 = 1,       // C_in == 32, C_out <= 64: K block = the 32 channels of one tap (64-byte rows, SWIZZLE_64B)
+  kLayoutPixelPairs = 2  // C_in == 32, 3x3 / stride 2 / pad 1 on even H, W: the input viewed as (N, H/2, [row parity], W/2, 64):
+                         // two horizontally adjacent pixels form one 64-channel "pixel pair", so the taps s = 1, 2 of a filter
+                         // row are ONE 128-byte-row K block (stride 1 in pair space) and s = 0 is the upper half of the
+                         // pair to the left: 6 K blocks of full 128-byte rows instead of 9 half-empty ones
 };
 
 struct ConvKernelParams {
@@ -30,6 +41,7 @@ struct ConvKernelParams {
   int stride, pad, dil;
   int m_tiles, n_tiles;
   int a_chan_from_n;  // grouped conv with 64-channel block-diagonal weights: A channel base = n_tile * 64
+  unsigned pair_taps; // kLayoutPixelPairs: per K block a nibble {8 valid | 4 row offset | 2 pair offset | 1 odd-row map}; 0 otherwise
   // epilogue: y = act2(act1(acc * scale + shift) + residual)
   const float* scale;
   const float* shift;
@@ -67,6 +79,7 @@ struct TcConvLaunch {
   ConvKernelParams p;
   int mode, block_n, grid, threads, smem, dual;
   int two;  // launched as CTA pairs (cluster of 2, tcgen05.mma.cta_group::2)
+  int kblock;    // channels per K block: 64, or 32 for 32-input-channel layers (0 = 64)
   int chain_n1;  // > 0: chain launch (conv -> 1x1 conv in one kernel), width of the first conv (64 or 128)
   int chain_w1res;  // chain launch keeps the first conv's weights resident in shared memory
 };
@@ -88,7 +101,9 @@ bool tc_chain_supported(int Cin, int N1, int N2);
 cudaError_t tc_conv_launch(const TcConvLaunch& L, cudaStream_t stream);
 cudaError_t tc_conv_set_attributes();
 // number of K elements per output channel in the packed weight matrix for this geometry
-int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode);
+int tc_conv_packed_k(int Cin, int R, int S, int groups, int mode, int layout = kLayoutPlain);
+// K layout for a dense conv of this geometry (kLayoutPlain for everything but 32-input-channel im2col layers)
+int tc_conv_layout(int Cin, int Cout, int R, int S, int stride, int pad, int dil, int groups, int H, int W);
 int tc_conv_mode(int Cin, int R, int S, int stride, int pad, int groups);
 
 // ---- stem conv (C_in <= 4) as a row-ring implicit GEMM, optional fused 3x3/s2/p1 max-pool ------------

@@ -454,13 +454,14 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   }
   // tensor-core path
   const int mode = tc_conv_mode(C, R, S, stride, pad, groups);
-  const int Ktot = tc_conv_packed_k(C, R, S, groups, mode);
+  const int layout = is_linear ? kLayoutPlain : tc_conv_layout(C, K, R, S, stride, pad, dil, groups, H, W);
+  const int Ktot = tc_conv_packed_k(C, R, S, groups, mode, layout);
   __nv_bfloat16* w = nullptr;
   if ((rc = dev_alloc(p, &w, static_cast<size_t>(K_pad) * Ktot)) != TLXCV_OK) return rc;
   if (is_linear)
     TLX_CUDA(ctx, pack_linear_weights(d.filters, w, C, K, K_pad, st));
   else
-    TLX_CUDA(ctx, pack_conv_weights(d.filters, w, K, K_pad, C, R, S, groups, mode, Ktot, st));
+    TLX_CUDA(ctx, pack_conv_weights(d.filters, w, K, K_pad, C, R, S, groups, layout == kLayoutPixelPairs ? kModePixelPairs : mode, Ktot, st));
   if (is_linear && Ktot != C)
     return fail(ctx, TLXCV_ERR_UNSUPPORTED, "linear: in_features (%d) must be a multiple of 64", C);
   op.weights = w;
@@ -516,8 +517,8 @@ int compile_conv(tlxcv_plan* p, OpRt& op, cudaStream_t st, bool is_linear) {
   op.impl = kImplTcConv;
   char name[48];
   static const char* mnames[] = {"tiled", "im2col", "gatherc4"};
-  snprintf(name, sizeof name, "conv_tcgen05_%s_n%d%s%s", mnames[op.tc.mode], op.tc.block_n, groups > 1 ? "_grouped" : "",
-           op.tc.two ? "_2sm" : "");
+  snprintf(name, sizeof name, "conv_tcgen05_%s_n%d%s%s%s", mnames[op.tc.mode], op.tc.block_n, groups > 1 ? "_grouped" : "",
+           op.tc.two ? "_2sm" : "", op.tc.kblock == 32 ? "_kb32" : (op.tc.p.pair_taps ? "_pixelpairs" : ""));
   // tensor-bound when arithmetic intensity exceeds the ridge (~248 FLOP/B on the measured peaks)
   set_info(op, name, 1, flops / bytes > 248.0 ? 1 : 0, flops, bytes, op.tc.grid, op.tc.threads, op.tc.smem, op.tc.block_n);
   return TLXCV_OK;

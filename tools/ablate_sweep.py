@@ -37,6 +37,11 @@ LAYERS = [  # name, cin, cout, hw, k, stride, res, env
     ("l3conv2_s2", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_STAGES": "2"}),
     ("l3conv2_s3", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_STAGES": "3"}),
     ("l3conv2_r4", 256, 256, 14, 3, 1, False, {"TLXCV_DEBUG_RING": "4"}),
+    # DarkNet-53 at 608x608, batch 64 ("_n")
+    ("dn_ds0", 32, 64, 608, 3, 2, False, {"_n": "64"}),
+    ("dn_ds0_kb64", 32, 64, 608, 3, 2, False, {"_n": "64", "TLXCV_NO_KB32": "1"}),
+    ("dn_ds1", 64, 128, 304, 3, 2, False, {"_n": "64"}),
+    ("dn_s1_3x3", 64, 128, 152, 3, 1, False, {"_n": "64"}),
 ]
 ABLATIONS = [int(x) for x in os.environ.get("ABLATIONS", "0,2,16,18,8,24,26,32,40,56,4,12").split(",")]
 
@@ -58,6 +63,7 @@ def main():
                 continue
             os.environ["TLXCV_DEBUG_ABLATE"] = str(ab)
             print(f"[{name} ablate={ab}]", file=sys.stderr, flush=True)
+            n = int(env.get("_n", 256))
             for kk, vv in env.items():
                 os.environ[kk] = vv
 
