@@ -37,6 +37,14 @@ constexpr int kABytes = kBlockM * kBlockK * 2;  // 16384
 constexpr int kEpiWarps = 8;                    // warps 2..9 (raise to 16 to experiment with p.epi_warps = 16: costs registers)
 constexpr int kGatherWarps = 8;                 // warps 10..17 (kModeGatherC4 only)
 constexpr int kMaxRing = 4;                     // per epilogue warp: ring of 2 or 4 (32 rows x 64 B) SWIZZLE_64B buffers
+#ifdef TLXCV_NARROW_ITEMS                       // A/B builds only
+constexpr bool kWideItems = false;
+#else
+constexpr bool kWideItems = true;               // 4-deep rings of 128/256-wide bf16 tiles run as two 4 KB slots of 32 x 64 items
+#endif
+constexpr int kWidePrefetchHalf = 0;            // wide items: the next item's residual is requested before this half of the item
+// host-side mirror of epilogue_loop's WIDE condition: the output / residual tensor maps then carry 64-column SWIZZLE_128B boxes
+inline bool wide_items(int ring, int block_n, bool out_bf16) { return kWideItems && ring == 4 && block_n >= 128 && out_bf16 && kEpiWarps == 8; }
 constexpr int kSmemLimit = 232448;              // 227 KB of dynamic shared memory per CTA
 constexpr int kScaleBufBytes = 2 * 256 * 4;      // [scale | shift] of one N tile; the kernel has sc_bufs (1 or 2) of them
 constexpr int kBarrierBytes = 1024;             // pipeline barriers + kEpiWarps * kRing residual barriers
@@ -252,8 +260,17 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
   // 8-warp build; a.cpw when kEpiWarps is raised for experiments)
   const int kCpw = kEpiWarps == 8 ? (BLOCK_N / 32) / 2 : a.cpw;
   const int c_first = cgroup * kCpw;
-  const int swz_own = (lane >> 1) & 3;
-  const uint32_t own_row = a.ring + lane * 64;
+  // WIDE items (the 4-deep ring of 128/256-wide bf16 tiles, i.e. residual and short-K layers, whose pace this loop sets):
+  // one item = 32 rows x 64 channels = TWO accumulator chunks behind ONE residual TMA load and ONE TMA store (128-byte
+  // rows, SWIZZLE_128B), in a ring of two 4 KB slots.  The per-item fixed costs (bulk-group wait, expect_tx + TMA issue,
+  // barrier wait, proxy fence, store issue + commit: ~900 of the ~1850 cycles of a 32-column item, tools/trace_chunks.py)
+  // are paid once per 64 columns.
+  constexpr bool WIDE = kWideItems && kRing == 4 && BLOCK_N >= 128 && !F32 && kEpiWarps == 8;
+  constexpr int kHalves = WIDE ? 2 : 1;            // accumulator chunks per item
+  constexpr int kSlotBytes = 2048 * kHalves;
+  constexpr uint32_t kSlots = WIDE ? 2 : kRing;    // ring slots
+  const int swz_own = WIDE ? (lane & 7) : ((lane >> 1) & 3);
+  const uint32_t own_row = a.ring + lane * (64 * kHalves);
 
   // prefetch cursor (only lane 0 advances it): walks the same item sequence, two items ahead (one for a 2-slot ring)
   // (m_pair, n_tile) of a tile index advance incrementally by (dm, dn) per tile_stride: an integer division per tile
@@ -273,6 +290,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     pf_m0 = m_tile * kBlockM + lg * 32;
     pf_n0 = n_tile * BLOCK_N;
     pf_nmy = min(min(kCpw, BLOCK_N / 32 - c_first), max(0, (a.Cout - (pf_n0 + c_first * 32) + 31) / 32));
+    if (WIDE) pf_nmy = (pf_nmy + 1) >> 1;  // items
   };
   auto pf_issue = [&]() {  // issue the residual load of the next valid item, if any
     while (pf_u < n_units && pf_ci >= pf_nmy) {
@@ -283,17 +301,17 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
       if (pf_u < n_units) pf_place();
     }
     if (pf_u >= n_units || (a.ablate & 16)) return;
-    const uint32_t slot = pf & (kRing - 1);
+    const uint32_t slot = pf & (kSlots - 1);
     const uint32_t bar = a.res_bar + slot * 8;
-    mbar_arrive_expect_tx(bar, 2048);
-    tma_load_2d(a.ring + slot * 2048, a.tmap_res, bar, pf_n0 + (c_first + pf_ci) * 32, pf_m0);
+    mbar_arrive_expect_tx(bar, kSlotBytes);
+    tma_load_2d(a.ring + slot * kSlotBytes, a.tmap_res, bar, pf_n0 + (c_first + pf_ci * kHalves) * 32, pf_m0);
     ++pf;
     ++pf_ci;
   };
   if (RES && lane == 0) {
     if (pf_u < n_units) pf_place();
 #pragma unroll
-    for (int k = 0; k < (kRing == 4 ? 2 : 1); ++k) pf_issue();
+    for (int k = 0; k < ((kRing == 4 && !WIDE) ? 2 : 1); ++k) pf_issue();
   }
 
   uint32_t it = 0;  // items processed
@@ -367,41 +385,53 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     };
     if (n_my == 0 && lane == 0) release_acc();  // nothing to read: release at once
     if (btracer) trace_c(a.trace, 2, tr);  // [5k+3] scale/shift staged, chunk loop starts
+    const int n_items = WIDE ? (n_my + 1) >> 1 : n_my;
 #pragma unroll 1
-    for (int ci = 0; ci < n_my; ++ci, ++it) {
+    for (int ii = 0; ii < n_items; ++ii, ++it) {
+      const uint32_t slot = it & (kSlots - 1);
+      const uint32_t row = own_row + slot * kSlotBytes;
+      const int cbase0 = n0 + (c_first + ii * kHalves) * 32;  // first channel of the item
+      if (ftracer) trace_c(a.trace, 2, tr);  // [6k] item start
+#pragma unroll
+     for (int hh = 0; hh < kHalves; ++hh) {
+      const int ci = ii * kHalves + hh;
       const int chunk = c_first + ci;
       const int cbase = n0 + chunk * 32;
-      const uint32_t slot = it & (kRing - 1);
+      const bool last_read = ii == n_items - 1 && hh == kHalves - 1;  // this warp's last read of the tile's accumulator
       uint32_t v[32];
-      if (ftracer) trace_c(a.trace, 2, tr);  // [6k] chunk start
       tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + chunk * 32, v);
       uint32_t v2[DUAL ? 32 : 1];
       if (DUAL) tmem_ld_32x32b_x32(a.tmem_base + (static_cast<uint32_t>(lg * 32) << 16) + acc * kAccCols + BLOCK_N + chunk * 32,
                                    reinterpret_cast<uint32_t(&)[32]>(v2));
       if (RES) {
-        if (kRing == 4 && lane == 0) {
+        if (kRing == 4 && !WIDE && lane == 0) {
           // four slots: [it-1] draining, [it] in use, [it+1] in flight; request item it+2 into the slot item it-2 used.
           // That store was committed a whole item ago, so this wait does not stall (waiting for the store just
           // committed cost ~300 cycles per item), and the request still leads its use by two items.
           asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           pf_issue();
         }
-        if (!(a.ablate & 16)) mbar_wait(a.res_bar + slot * 8, (it / kRing) & 1);  // residual chunk has landed in the ring slot
-      } else if (!F32) {
-        // the TMA store that used this slot kRing items ago must have finished reading it
+        if (WIDE && hh == kWidePrefetchHalf && lane == 0) {
+          // two slots: request item it+1 into the slot item it-1 used, once that item's store has read it
+          asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          pf_issue();
+        }
+        if (hh == 0 && !(a.ablate & 16)) mbar_wait(a.res_bar + slot * 8, (it / kSlots) & 1);  // residual item has landed in the ring slot
+      } else if (!F32 && hh == 0) {
+        // the TMA store that used this slot kSlots items ago must have finished reading it
         if (lane == 0) {
-          if (kRing == 4)
+          if (kSlots == 4)
             asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
           else
             asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
         }
         __syncwarp();
       }
-      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+1] residual landed / staging slot free
+      if (ftracer && hh == 0) trace_c(a.trace, 2, tr);  // [6k+1] residual landed / staging slot free
       tmem_ld_wait();
-      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+2] accumulator chunk in registers
+      if (ftracer && hh == 0) trace_c(a.trace, 2, tr);  // [6k+2] accumulator chunk in registers
       if (a.ablate & 32) {  // timing experiment: accumulator read and dropped
-        if (ci == n_my - 1) {
+        if (last_read) {
           tcgen05_fence_before();
           __syncwarp();
           if (lane == 0) release_acc();
@@ -459,7 +489,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
           pr[2 * j + 1] = ffma2(pack_u64(v[4 * j + 2], v[4 * j + 3]), sc.y, sh.y);
         }
       }
-      if (ci == n_my - 1) {
+      if (last_read) {
         // this warp's last read of the accumulator and of the tile's scale/shift buffer: hand the TMEM
         // buffer back to the MMA warp (one arrival per warp: 256 same-address smem atomics per tile were a
         // measurable cost)
@@ -507,8 +537,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         }
         continue;
       }
-      const uint32_t row = own_row + slot * 2048;
-      if (ftracer) trace_c(a.trace, 2, tr);  // [6k+3] scale/shift/act done (approximately: the compiler may move math)
+      if (ftracer && hh == kHalves - 1) trace_c(a.trace, 2, tr);  // [6k+3] scale/shift/act done (approximately: the compiler may move math)
       uint4 rv[RES ? 4 : 1];
       if (RES) {
         // the four 16-byte pieces of this lane's residual row, requested back to back (volatile asm keeps program order:
@@ -517,11 +546,11 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         for (int j = 0; j < 4; ++j)
           asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
                        : "=r"(rv[j % (RES ? 4 : 1)].x), "=r"(rv[j % (RES ? 4 : 1)].y), "=r"(rv[j % (RES ? 4 : 1)].z), "=r"(rv[j % (RES ? 4 : 1)].w)
-                       : "r"(row + ((j ^ swz_own) << 4)));
+                       : "r"(row + (((4 * hh + j) ^ swz_own) << 4)));
       }
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
-        const uint32_t addr = row + ((j ^ swz_own) << 4);
+        const uint32_t addr = row + (((4 * hh + j) ^ swz_own) << 4);
         uint32_t o[4];
         if (RES) {
           const uint4 val = rv[j % (RES ? 4 : 1)];
@@ -543,11 +572,13 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
         // residual read and this write
         asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(o[0]), "r"(o[1]), "r"(o[2]), "r"(o[3]) : "memory");
       }
+     }  // halves
+      if (F32 || (a.ablate & 32)) continue;
       if (!(a.ablate & 128)) fence_proxy_async_smem();  // generic-proxy stores -> visible to the TMA (async proxy) read
       __syncwarp();
       if (ftracer) trace_c(a.trace, 2, tr);  // [6k+4] staged
       if (lane == 0) {
-        if (!(a.ablate & 2)) tma_store_2d(a.tmap_out, a.ring + slot * 2048, cbase, m0);
+        if (!(a.ablate & 2)) tma_store_2d(a.tmap_out, a.ring + slot * kSlotBytes, cbase0, m0);
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
         if (RES && kRing == 2) {
           // two slots: refill the slot item it-1 used with item it+1 as soon as its store has read the buffer
@@ -666,7 +697,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       const int PQ = p.P * p.Q;
       int tr = 0;
       for (int tile = worker; tile < num_tiles; tile += n_workers) {
-        trace_c(p.trace, 0, tr);  // [2k] tile start
+        if (!(p.ablate & 512)) trace_c(p.trace, 0, tr);  // [2k] tile start
         const int m_pair = tile / p.n_tiles, n_tile = tile - m_pair * p.n_tiles;
         const int m_tile = TWO ? 2 * m_pair + static_cast<int>(rank) : m_pair;  // a pair's second tile may lie past M: zero-filled
         const int m0 = m_tile * kBlockM, n0 = n_tile * BLOCK_N;
@@ -682,7 +713,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // no divisions in the K loop: this single thread's per-iteration latency bounds small-N tiles
         int r = 0, sx = 0, cb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
+#ifdef TLXCV_FINE_TRACE
+          if (p.ablate & 512) trace_c(p.trace, 0, tr);  // round trace: before the empty wait
+#endif
           mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+#ifdef TLXCV_FINE_TRACE
+          if (p.ablate & 512) trace_c(p.trace, 0, tr);  // round trace: slot free
+#endif
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
           const uint32_t a_dst = smem_u32(smem + ps.stage * kStageB);
           if constexpr (TWO) {
@@ -743,7 +780,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           tma_load_2d(a_dst + kAB, &tmapB, bar, kb * KB, n0);
           ps.advance(n_stages);
         }
-        trace_c(p.trace, 0, tr);  // [2k+1] all loads of the tile issued
+        if (!(p.ablate & 512)) trace_c(p.trace, 0, tr);  // [2k+1] all loads of the tile issued
       }
     }
   } else if (warp == 1) {
@@ -757,10 +794,18 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
       // (64-byte rows: 8-row atoms of 512 B, SWIZZLE_64B)
       constexpr uint32_t desc_hi = KB == 64 ? ((1024u >> 4) | (1u << 14) | (2u << 29)) : ((512u >> 4) | (1u << 14) | (4u << 29));
       const uint32_t smem_lo = ((smem_u32(smem) & 0x3FFFFu) >> 4) | (1u << 16);  // descriptor low word of stage 0
-      const bool tracer1 = lane == 0 && p.trace != nullptr;
+      const bool rtrace = (p.ablate & 512) != 0;  // per-round events instead of per-tile events (fine trace builds)
+      const bool tracer1 = lane == 0 && p.trace != nullptr && !rtrace;
+#ifdef TLXCV_FINE_TRACE
+      const bool rtracer = lane == 0 && p.trace != nullptr && rtrace;
+#endif
       const uint32_t full0 = smem_u32(full_bar), empty0 = smem_u32(empty_bar);
       const int num_kb = p.num_kb, num_kb1 = p.num_kb1;
-      const bool no_mma = (p.ablate & 4) != 0;
+#ifdef TLXCV_DEBUG_TOOLS
+      const bool no_mma = (p.ablate & 4) != 0;  // timing experiments
+#else
+      constexpr bool no_mma = false;
+#endif
       PipeState ps;
       uint32_t acc = 0, acc_phase = 0;
       int tr = 0;
@@ -775,7 +820,13 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         // of a 128-wide K block.
         for (int kb = 0; kb < num_kb;) {
           const uint32_t st0 = ps.stage;
+#ifdef TLXCV_FINE_TRACE
+          if (rtracer) trace_c(p.trace, 1, tr);  // round trace: before the full wait
+#endif
           mbar_wait(full0 + st0 * 8, ps.phase);
+#ifdef TLXCV_FINE_TRACE
+          if (rtracer) trace_c(p.trace, 1, tr);  // round trace: operands landed
+#endif
           ps.advance(n_stages);
           const uint32_t st1 = ps.stage;
           // the next K block joins this round only if its operands have landed already (never wait for it: with three
@@ -784,44 +835,56 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           if (two_kb) ps.advance(n_stages);
           tcgen05_fence_after();
           if (kb == 0 && tracer1) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
-          if (elect_one_sync()) {
+          // The elected block is straight-line code: a conditional commit (or a loop with a break) inside it costs ~100
+          // cycles per round in divergence bookkeeping (tools/micro/ctrl_cost4.cu), so the one / two K block cases branch
+          // OUTSIDE the election (warp-uniform) and the accumulator hand-over has its own election after the K loop.
+          auto issue_kb = [&](int kk, uint32_t st) {
+            const bool second = DUAL && kk >= num_kb1;
+            const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
+            const int kbl = second ? kk - num_kb1 : kk;  // first K block of an accumulator overwrites it
+            const uint32_t a_lo = smem_lo + st * (kStageB >> 4);
+            const uint32_t b_lo = a_lo + (kAB >> 4);
+            if (!no_mma) {
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-              if (h == 1 && !two_kb) break;
-              const int kk = kb + h;
-              const uint32_t st = h ? st1 : st0;
-              const bool second = DUAL && kk >= num_kb1;
-              const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
-              const int kbl = second ? kk - num_kb1 : kk;  // first K block of an accumulator overwrites it
-              const uint32_t a_lo = smem_lo + st * (kStageB >> 4);
-              const uint32_t b_lo = a_lo + (kAB >> 4);
-              if (!no_mma) {
-#pragma unroll
-                for (int k = 0; k < KB / 16; ++k) {
-                  // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
-                  if (k == 0)
-                    umma_bf16_lohi<TWO>(tmem_d, a_lo, b_lo, desc_hi, idesc, kbl != 0);
-                  else
-                    umma_bf16_lohi<TWO>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
-                }
+              for (int k = 0; k < KB / 16; ++k) {
+                // +32 B per 16-element K step inside the 128 B swizzle atom: +2 in the (addr >> 4) field
+                if (k == 0)
+                  umma_bf16_lohi<TWO>(tmem_d, a_lo, b_lo, desc_hi, idesc, kbl != 0);
+                else
+                  umma_bf16_lohi<TWO>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
               }
-              // frees the smem stage (of both CTAs of a pair) when these MMAs retire
-              if (TWO)
-                umma_commit_2sm(empty0 + st * 8);
-              else
-                umma_commit(empty0 + st * 8);
             }
-            // accumulator ready for the epilogue (of both CTAs of a pair)
-            if (kb + (two_kb ? 2 : 1) >= num_kb) {
-              if (TWO)
-                umma_commit_2sm(smem_u32(&tmem_full_bar[acc]));
-              else
-                umma_commit(smem_u32(&tmem_full_bar[acc]));
+            // frees the smem stage (of both CTAs of a pair) when these MMAs retire
+            if (TWO)
+              umma_commit_2sm(empty0 + st * 8);
+            else
+              umma_commit(empty0 + st * 8);
+          };
+          if (two_kb) {
+            if (elect_one_sync()) {
+              issue_kb(kb, st0);
+              issue_kb(kb + 1, st1);
             }
+          } else {
+            if (elect_one_sync()) issue_kb(kb, st0);
           }
           __syncwarp();
+#ifdef TLXCV_FINE_TRACE
+          if (rtracer) {
+            trace_c(p.trace, 1, tr);  // round trace: round issued + committed
+            if (blockIdx.x == 0 && tr < kTraceLenC) p.trace[kTraceLenC + tr++] = two_kb ? 2 : 1;  // K blocks in this round
+          }
+#endif
           kb += two_kb ? 2 : 1;
         }
+        // accumulator ready for the epilogue (of both CTAs of a pair)
+        if (elect_one_sync()) {
+          if (TWO)
+            umma_commit_2sm(smem_u32(&tmem_full_bar[acc]));
+          else
+            umma_commit(smem_u32(&tmem_full_bar[acc]));
+        }
+        __syncwarp();
         if (tracer1) trace_c(p.trace, 1, tr);  // [4k+3] all MMAs of the tile issued
         if (++acc == 2) {
           acc = 0;
@@ -1153,6 +1216,11 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         for (int kb2 = 0; kb2 < kKb2; ++kb2) {
           mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
+          if (p.ablate & 8) {  // timing experiment (debug builds): operands never loaded
+            mbar_arrive(bar);
+            ps.advance(n_stages);
+            continue;
+          }
           mbar_arrive_expect_tx(bar, kABytes);
           tma_load_2d(smem_u32(smem + ps.stage * CC::kSlot), &tmapB2, bar, kb2 * kBlockK, c * BLOCK_N);
           ps.advance(n_stages);
@@ -1162,18 +1230,29 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         mbar_arrive_expect_tx(smem_u32(w1_full_bar), p.num_kb1 * CC::kB1Bytes);
         for (int kb = 0; kb < p.num_kb1; ++kb) tma_load_2d(smem_u32(w1res + kb * CC::kB1Bytes), &tmapB, smem_u32(w1_full_bar), kb * kBlockK, 0);
       }
+      int tr = 0;
       for (int i = 0; i < my_tiles; ++i) {
+        trace_c(p.trace, 0, tr);  // [2i] tile start
         const int m0 = (worker + i * n_workers) * kBlockM;
         const int img = m0 / PQ;
         const int rem = m0 - img * PQ;
         const int op = rem / p.Q, oq = rem - op * p.Q;
         const int base_h = op * p.stride - p.pad, base_w = oq * p.stride - p.pad;
         int r = 0, sx = 0, cb = 0, c_next = 0;
+        int slot_at = p.num_kb1 / (n_chunks + 1);  // K block in front of which the next G2 chunk goes (no division per K block)
         for (int kb = 0; kb < p.num_kb1; ++kb) {
-          if (i > 0 && c_next < n_chunks && kb == ((c_next + 1) * p.num_kb1) / (n_chunks + 1)) load_g2_chunk(c_next++);
+          if (i > 0 && c_next < n_chunks && kb == slot_at) {
+            load_g2_chunk(c_next++);
+            slot_at = ((c_next + 1) * p.num_kb1) / (n_chunks + 1);
+          }
           mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
           const uint32_t dst = smem_u32(smem + ps.stage * CC::kSlot);
+          if (p.ablate & 8) {  // timing experiment (debug builds): operands never loaded
+            mbar_arrive(bar);
+            ps.advance(n_stages);
+            continue;
+          }
           mbar_arrive_expect_tx(bar, CC::kSlot);  // == kABytes when the weights are resident
           tma_load_im2col_4d(dst, &tmapA, bar, cb * kBlockK, base_w, base_h, img, static_cast<uint16_t>(sx * p.dil),
                              static_cast<uint16_t>(r * p.dil));
@@ -1186,6 +1265,7 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         }
         if (i > 0)
           while (c_next < n_chunks) load_g2_chunk(c_next++);
+        trace_c(p.trace, 0, tr);  // [2i+1] all loads of the tile issued
       }
       if (my_tiles > 0)
         for (int c = 0; c < n_chunks; ++c) load_g2_chunk(c);
@@ -1205,13 +1285,23 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
       mbar_wait(smem_u32(w1_full_bar), 0);
       tcgen05_fence_after();
     }
+    int tr = 0;
+    const bool tracer1 = lane == 0 && p.trace != nullptr;
+#ifdef TLXCV_DEBUG_TOOLS
+    const bool no_mma = (p.ablate & 4) != 0;  // timing experiments
+#else
+    constexpr bool no_mma = false;
+#endif
     auto issue_g2_chunk = [&](uint32_t j, int c) {
       if (c == 0) {
+        if (tracer1) trace_c(p.trace, 1, tr);  // [6i+2] before the A2 wait
         mbar_wait(smem_u32(a2_full_bar), j & 1u);  // the epilogue warps have written A2 of tile j
         tcgen05_fence_after();
+        if (tracer1) trace_c(p.trace, 1, tr);  // [6i+3] A2 of the previous tile is ready
       }
       mbar_wait(smem_u32(&tmem_empty_bar[acc2]), acc2_phase ^ 1);
       tcgen05_fence_after();
+      if (c == 0 && tracer1) trace_c(p.trace, 1, tr);  // [6i+4] acc2 buffer free
       const uint32_t tmem_d = tmem_base + acc2 * BLOCK_N;
       for (int kb2 = 0; kb2 < kKb2; ++kb2) {
         const uint32_t st = ps.stage;
@@ -1221,29 +1311,41 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (elect_one_sync()) {
           const uint32_t a_lo = a2_lo + kb2 * (kABytes >> 4);
           const uint32_t b_lo = smem_lo + st * (CC::kSlot >> 4);
+          if (!no_mma)
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_bf16_lohi<false>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc2, (kb2 != 0 || k != 0) ? 1u : 0u);
           umma_commit(empty0 + st * 8);
-          if (kb2 == kKb2 - 1) {
-            umma_commit(smem_u32(&tmem_full_bar[acc2]));
-            if (c == n_chunks - 1) umma_commit(smem_u32(a2_empty_bar));  // every MMA that reads A2 of this tile has retired
-          }
         }
         __syncwarp();
       }
+      // hand-overs outside the per-K-block election (a conditional commit inside it costs ~100 cycles per round)
+      if (c == n_chunks - 1) {
+        if (elect_one_sync()) {
+          umma_commit(smem_u32(&tmem_full_bar[acc2]));
+          umma_commit(smem_u32(a2_empty_bar));  // every MMA that reads A2 of this tile has retired
+        }
+      } else {
+        if (elect_one_sync()) umma_commit(smem_u32(&tmem_full_bar[acc2]));
+      }
+      __syncwarp();
       if (++acc2 == 2) acc2 = 0, acc2_phase ^= 1;
     };
     for (int i = 0; i < my_tiles; ++i) {
       const uint32_t b = static_cast<uint32_t>(i) & 1u;
+      if (tracer1) trace_c(p.trace, 1, tr);  // [6i] tile start
       mbar_wait(smem_u32(&acc1_empty_bar[b]), ((static_cast<uint32_t>(i) >> 1) & 1u) ^ 1u);
       tcgen05_fence_after();
+      if (tracer1) trace_c(p.trace, 1, tr);  // [6i+1] acc1 buffer free
+      if (i == 0 && tracer1) { trace_c(p.trace, 1, tr); trace_c(p.trace, 1, tr); trace_c(p.trace, 1, tr); }  // no G2 inside the first tile
       const uint32_t tmem_d = tmem_base + 256u + b * N1;
       int c_next = 0;
+      int slot_at = p.num_kb1 / (n_chunks + 1);
       for (int kb = 0; kb < p.num_kb1; ++kb) {
-        if (i > 0 && c_next < n_chunks && kb == ((c_next + 1) * p.num_kb1) / (n_chunks + 1)) {
+        if (i > 0 && c_next < n_chunks && kb == slot_at) {
           issue_g2_chunk(static_cast<uint32_t>(i - 1), c_next);
           ++c_next;
+          slot_at = ((c_next + 1) * p.num_kb1) / (n_chunks + 1);
         }
         const uint32_t st = ps.stage;
         mbar_wait(full0 + st * 8, ps.phase);
@@ -1252,16 +1354,19 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
         if (elect_one_sync()) {
           const uint32_t a_lo = smem_lo + st * (CC::kSlot >> 4);
           const uint32_t b_lo = W1RES ? w1_lo + kb * (CC::kB1Bytes >> 4) : a_lo + (kABytes >> 4);
+          if (!no_mma)
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k)
             umma_bf16_lohi<false>(tmem_d, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc1, (kb != 0 || k != 0) ? 1u : 0u);
           umma_commit(empty0 + st * 8);
-          if (kb == p.num_kb1 - 1) umma_commit(smem_u32(&acc1_full_bar[b]));
         }
         __syncwarp();
       }
+      if (elect_one_sync()) umma_commit(smem_u32(&acc1_full_bar[b]));  // first GEMM of the tile complete -> epilogue warps (chain_e1)
+      __syncwarp();
       if (i > 0)
         for (; c_next < n_chunks; ++c_next) issue_g2_chunk(static_cast<uint32_t>(i - 1), c_next);
+      if (tracer1) trace_c(p.trace, 1, tr);  // [6i+5] all MMAs of the iteration issued
     }
     if (my_tiles > 0)
       for (int c = 0; c < n_chunks; ++c) issue_g2_chunk(static_cast<uint32_t>(my_tiles - 1), c);
@@ -1286,7 +1391,7 @@ conv_chain_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_consta
     a.two = 0, a.rank = 0, a.tmem_empty_remote = 0;
     a.alpha1 = p.alpha1, a.alpha2 = p.alpha2;
     a.ablate = p.ablate;
-    a.trace = nullptr;
+    a.trace = p.trace;
     a.chain_m_tiles = m_tiles;
     a.acc1_full_bar = smem_u32(acc1_full_bar), a.acc1_empty_bar = smem_u32(acc1_empty_bar);
     a.a2_full_bar = smem_u32(a2_full_bar), a.a2_empty_bar = smem_u32(a2_empty_bar);
@@ -1666,10 +1771,13 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
     L.tmapA = L.tmapB;  // unused
   }
   if (!err.empty()) return err;
-  // output [M][Cout] bf16 written by per-warp TMA stores of 32 rows x 32 channels (64 B rows, SWIZZLE_64B);
+  // output [M][Cout] bf16 written by per-warp TMA stores of 32 rows x 32 channels (64 B rows, SWIZZLE_64B) or, for the
+  // wide items of a 4-deep ring, 32 rows x 64 channels (128 B rows, SWIZZLE_128B);
   // fp32 outputs (logits) are written with direct stores and leave the map unused
+  const bool wide = wide_items(p.ring, block_n, out_bf16 != nullptr);
   if (out_bf16)
-    err = encode_2d(&L.tmapOut, out_bf16, Cout, p.M, static_cast<uint64_t>(Cout_storage) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    err = encode_2d(&L.tmapOut, out_bf16, Cout, p.M, static_cast<uint64_t>(Cout_storage) * 2, wide ? 64 : 32, 32,
+                    wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
   else
     L.tmapOut = L.tmapB;
   if (!err.empty()) return err;
@@ -1677,7 +1785,8 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   if (residual_bf16) {
     if (!out_bf16) return "conv: a residual needs a bf16 output";
     if (mode == kModeGatherC4) return "stem conv: residual inputs are not supported";
-    err = encode_2d(&L.tmapRes, residual_bf16, Cout, p.M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    err = encode_2d(&L.tmapRes, residual_bf16, Cout, p.M, static_cast<uint64_t>(Cout) * 2, wide ? 64 : 32, 32,
+                    wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B);
     p.residual = static_cast<const __nv_bfloat16*>(residual_bf16);
   } else {
     L.tmapRes = L.tmapB;
@@ -1725,7 +1834,9 @@ std::string tc_conv_prepare_dual(TcConvLaunch& L, int sm_count, const __nv_bfloa
   else
     err = encode_2d(&L.tmapA2, a2, C2, M, static_cast<uint64_t>(C2) * 2, kBlockK, kBlockM);
   if (!err.empty()) return err;
-  if (!(err = encode_2d(&L.tmapOut, out_bf16, Cout, M, static_cast<uint64_t>(Cout) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)).empty())
+  const bool wide = wide_items(p.ring, block_n, true);
+  if (!(err = encode_2d(&L.tmapOut, out_bf16, Cout, M, static_cast<uint64_t>(Cout) * 2, wide ? 64 : 32, 32,
+                        wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)).empty())
     return err;
   L.tmapRes = L.tmapB;
   return "";
@@ -1780,10 +1891,13 @@ std::string tc_chain_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16*
   if (!(err = encode_2d(&L.tmapB, w1, K1tot, 256, static_cast<uint64_t>(K1tot) * 2, kBlockK, N1)).empty()) return err;
   if (!(err = encode_2d(&L.tmapB2, w2, N1, n2_pad, static_cast<uint64_t>(N1) * 2, kBlockK, block_n)).empty()) return err;
   if (!(err = encode_im2col(&L.tmapA, act_in, N, H, W, Cin, R, S, stride, pad, dil)).empty()) return err;
-  if (!(err = encode_2d(&L.tmapOut, out_bf16, N2, p.M, static_cast<uint64_t>(N2) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)).empty())
+  const bool wide = wide_items(p.ring, block_n, true);
+  if (!(err = encode_2d(&L.tmapOut, out_bf16, N2, p.M, static_cast<uint64_t>(N2) * 2, wide ? 64 : 32, 32,
+                        wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)).empty())
     return err;
   if (residual_bf16) {
-    if (!(err = encode_2d(&L.tmapRes, residual_bf16, N2, p.M, static_cast<uint64_t>(N2) * 2, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)).empty())
+    if (!(err = encode_2d(&L.tmapRes, residual_bf16, N2, p.M, static_cast<uint64_t>(N2) * 2, wide ? 64 : 32, 32,
+                          wide ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B)).empty())
       return err;
     p.residual = static_cast<const __nv_bfloat16*>(residual_bf16);
   } else {
@@ -1795,6 +1909,24 @@ std::string tc_chain_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16*
 
 template <int N1, bool W1RES>
 cudaError_t launch_chain(const TcConvLaunch& L, cudaStream_t st) {
+  // debugging (debug builds): CTA 0's timeline of the last chain launch, TLXCV_DEBUG_TRACE_CHAIN=<file> (tools/trace_chain.py)
+  static const char* trace_path = debug_env("TLXCV_DEBUG_TRACE_CHAIN");
+  if (trace_path != nullptr) {
+    static unsigned long long* dbuf = nullptr;
+    if (!dbuf) cudaMalloc(&dbuf, 3 * kTraceLenC * sizeof(unsigned long long));
+    cudaMemsetAsync(dbuf, 0, 3 * kTraceLenC * sizeof(unsigned long long), st);
+    ConvKernelParams p = L.p;
+    p.trace = dbuf;
+    conv_chain_kernel<N1, W1RES><<<L.grid, L.threads, L.smem, st>>>(L.tmapA, L.tmapB, L.tmapB2, L.tmapOut, L.tmapRes, p);
+    cudaStreamSynchronize(st);
+    std::vector<unsigned long long> h(3 * kTraceLenC);
+    cudaMemcpy(h.data(), dbuf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(trace_path, "wb")) {
+      fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+      fclose(f);
+    }
+    return cudaGetLastError();
+  }
   return launch_pdl(conv_chain_kernel<N1, W1RES>, L.grid, L.threads, L.smem, st, L.tmapA, L.tmapB, L.tmapB2, L.tmapOut, L.tmapRes, L.p);
 }
 

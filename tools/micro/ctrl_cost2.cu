@@ -26,10 +26,11 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 template <int V>
-__global__ void __launch_bounds__(64, 1) ctrl_kernel(int rounds, int stages, long long* out) {
-  __shared__ uint64_t full[16], empty[16];
+__global__ void __launch_bounds__(320, 1) ctrl_kernel(int rounds, int stages, long long* out, int spin_lanes) {
+  __shared__ uint64_t full[16], empty[16], never;
   if (threadIdx.x == 0) {
     for (int i = 0; i < 16; ++i) mbar_init(smem_u32(&full[i]), 1), mbar_init(smem_u32(&empty[i]), 1);
+    mbar_init(smem_u32(&never), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -46,6 +47,22 @@ __global__ void __launch_bounds__(64, 1) ctrl_kernel(int rounds, int stages, lon
       }
       out[1] = clock64() - t0;
     }
+  } else if (warp >= 2) {
+    // idle epilogue warps: spin_lanes lanes of each warp poll a barrier that completes only when the consumer is done
+    if (spin_lanes == 64) {
+      // "busy epilogue" stand-in: a long straight-line instruction stream (~16 K instructions per pass) executed until the consumer is done
+      float x0 = lane, x1 = lane + 1, x2 = lane + 2, x3 = lane + 3;
+      while (!mbar_try(smem_u32(&never), 0)) {
+#pragma unroll
+        for (int i = 0; i < 4096; ++i) {
+          x0 = fmaf(x0, 1.0001f, 0.5f + i);
+          x1 = fmaf(x1, 0.9999f, 0.25f + i);
+          x2 = fmaf(x2, 1.0002f, 0.125f + i);
+          x3 = fmaf(x3, 0.9998f, 0.0625f + i);
+        }
+      }
+      if (x0 + x1 + x2 + x3 == 12345.678f) out[3] = 1;
+    } else if (lane < spin_lanes) mbar_wait(smem_u32(&never), 0);
   } else {
     if ((V & 2) || lane == 0) {
       int s = 0, ph = 0;
@@ -62,16 +79,19 @@ __global__ void __launch_bounds__(64, 1) ctrl_kernel(int rounds, int stages, lon
         }
         if (++s == stages) s = 0, ph ^= 1;
       }
-      if (lane == 0) out[0] = clock64() - t0;
+      if (lane == 0) {
+        out[0] = clock64() - t0;
+        mbar_arrive(smem_u32(&never));
+      }
     }
   }
 }
 
 template <int V>
-void run(long long* d) {
+void run(long long* d, int grid, int spin_lanes) {
   const int rounds = 20000;
   for (int stages : {2, 6}) {
-    ctrl_kernel<V><<<1, 64>>>(rounds, stages, d);
+    ctrl_kernel<V><<<grid, 320>>>(rounds, stages, d, spin_lanes);
     cudaError_t e = cudaDeviceSynchronize();
     long long h[2];
     cudaMemcpy(h, d, sizeof h, cudaMemcpyDeviceToHost);
@@ -83,8 +103,8 @@ void run(long long* d) {
 
 int main() {
   long long* d;
-  cudaMalloc(&d, 2 * sizeof(long long));
+  cudaMalloc(&d, 8 * sizeof(long long));
   setvbuf(stdout, nullptr, _IONBF, 0);
-  run<0>(d); run<1>(d); run<2>(d); run<3>(d); run<4>(d); run<5>(d); run<7>(d);
+  for (int spin : {0, 32, 64}) { printf("8 idle warps, %d lanes of each polling\n", spin); run<0>(d, 148, spin); run<1>(d, 148, spin); run<3>(d, 148, spin); run<7>(d, 148, spin); }
   return 0;
 }
