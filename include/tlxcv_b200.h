@@ -20,6 +20,9 @@
  *   nn.MaxPool2d                                                    TLXCV_OP_MAXPOOL
  *   nn.AdaptiveAvgPool2d(1)                                         TLXCV_OP_GAP
  *   nn.AvgPool2d(2, 2)   segmentation/backbones/resnet_vd.py:25-27  TLXCV_OP_AVGPOOL
+ *   nn.AvgPool2d(3, 2, 1) classification/resnest.py:245-250         TLXCV_OP_AVGPOOL (pad = 1)
+ *   SplatConv.forward    classification/resnest.py:146-166          TLXCV_OP_CONV (dense 3x3) + TLXCV_OP_GAP + 2 x
+ *                                                                   TLXCV_OP_CONV (1x1) + TLXCV_OP_SPLAT_APPLY
  *   nn.Linear                                                       TLXCV_OP_LINEAR
  *   tlx.losses.softmax_cross_entropy_with_logits  tasks/image_classification.py:14  TLXCV_OP_SOFTMAX_CE
  *   Interpolater (nearest x2) + tlx.concat  detection/yolov3.py:244,252  TLXCV_OP_UPSAMPLE_CONCAT
@@ -85,7 +88,10 @@ typedef enum {
                                  times (in1 = -1: up-sampling alone; r = s = 1: channel concat): Interpolater +
                                  tlx.concat of YOLOv3FPN.forward (detection/yolov3.py:244,252-253) in one pass          */
   TLXCV_OP_SOFTMAX = 10,     /* (N, K) fp32 logits -> (N, K) fp32 probabilities (softmax over the class axis)           */
-  TLXCV_OP_AVGPOOL = 12,     /* AvgPool2d(k, stride) without padding (ResNet_vd shortcut, segmentation/backbones/resnet_vd.py:25-27) */
+  TLXCV_OP_AVGPOOL = 12,     /* AvgPool2d(k, stride, pad), padding counted as zeros (ResNet_vd / ResNeSt shortcut, segmentation/backbones/resnet_vd.py:25-27;
+                                ResNeSt avd pool 3x3 / 2 / 1, classification/resnest.py:245-250) */
+  TLXCV_OP_SPLAT_APPLY = 13, /* ResNeSt split attention (classification/resnest.py:53-82,146-166): in0 = (N, radix*C, H, W) map, in1 = (N, radix*C, 1, 1)
+                                attention logits, r = radix, groups = cardinality; out[n,c] = sum_r softmax_r(in1)[r,c] * in0[n, r*C + c] */
   TLXCV_OP_SOFTMAX_CE = 11   /* in0 = (N, K) fp32 logits, in1 = (N) int64 labels -> (1) fp32 mean cross-entropy:
                                  tlx.losses.softmax_cross_entropy_with_logits (tasks/image_classification.py:10-15)        */
 } tlxcv_op_kind;

@@ -19,6 +19,7 @@ REFERENCE_ROOT = os.environ.get("TLXCV_REFERENCE", "/root/reference")
 _FILES = {
     "resnet": "tlxcv/models/classification/resnet.py",
     "resnext": "tlxcv/models/classification/resnext.py",
+    "resnest": "tlxcv/models/classification/resnest.py",
     "mobilenetv1": "tlxcv/models/classification/mobilenetv1.py",
     "mobilenetv2": "tlxcv/models/classification/mobilenetv2.py",
     "darknet53": "tlxcv/models/classification/darknet53.py",
@@ -162,6 +163,9 @@ MODELS = {
     "wide_resnet50_2": ("resnet", "wide_resnet50_2", {}),
     "resnext50_32x4d": ("resnext", "resnext50_32x4d", {}),
     "resnext50_64x4d": ("resnext", "resnext50_64x4d", {}),
+    "resnest50": ("resnest", "resnest50", {}),
+    "resnest50_fast_1s1x64d": ("resnest", "resnest50_fast_1s1x64d", {}),
+    "resnest101": ("resnest", "resnest101", {}),
     "mobilenet_v1": ("mobilenetv1", "MobileNetV1", {}),
     "mobilenet_v2": ("mobilenetv2", "mobilenet_v2", {}),
     "darknet53_cls": ("darknet53", "darknet53", {}),

@@ -360,7 +360,59 @@ def resnet_vd(sd, x, layers=50, output_stride=8, taps=None):
     return feats
 
 
+def resnest(sd, x, layers=(3, 4, 6, 3), radix=2, cardinality=1, taps=None):
+    """classification/resnest.py:672-682 with the resnest50 / resnest101 options (:707-733: radix 2, deep stem, avg_down,
+    avd after the SplatConv): ConvBNLayer :47-50, rSoftmax :64-82, SplatConv :146-166, BottleneckBlock :312-328."""
+    p = _P(sd, "", taps)
+
+    def cbl(q, x, k, stride=1, groups=1, act=None):
+        return bn(q.sub("batch_norm"), conv(q.sub("_conv"), x, stride, (k - 1) // 2, groups), act)
+
+    def splat(q, x):
+        y = cbl(q.sub("conv1"), x, 3, 1, cardinality * radix, "relu")            # :147
+        parts = torch.chunk(y, radix, dim=1)                                     # :149-150
+        gap = parts[0]
+        for t in parts[1:]:
+            gap = gap + t                                                        # add_n :151
+        gap = F.adaptive_avg_pool2d(gap, 1)                                      # :154
+        att = conv(q.sub("conv3"), cbl(q.sub("conv2"), gap, 1, 1, cardinality, "relu"), 1, 0, cardinality)   # :155-156
+        b = att.shape[0]
+        att = att.reshape(b, cardinality, radix, -1).permute(0, 2, 1, 3)         # rSoftmax :72-75
+        att = F.softmax(att, dim=1).reshape(b, -1, 1, 1)                         # :76-77
+        out = None
+        for a, t in zip(torch.chunk(att, radix, dim=1), parts):                  # :159-162
+            out = t * a if out is None else out + t * a
+        return out
+
+    y = cbl(p.sub("stem.conv1"), x, 3, 2, 1, "relu")
+    y = cbl(p.sub("stem.conv2"), y, 3, 1, 1, "relu")
+    y = cbl(p.sub("stem.conv3"), y, 3, 1, 1, "relu")
+    y = F.max_pool2d(y, 3, 2, 1)
+    inplanes = y.shape[1]
+    for li, n in enumerate(layers):
+        planes = 64 << li
+        for i in range(n):
+            stride = 2 if (i == 0 and li > 0) else 1
+            is_first = i == 0 and li > 0                                         # ResNeStLayer(is_first=...) :546,560 (default True)
+            bp = p.sub(f"layer{li + 1}.layer{li + 1}_bottleneck_{i}")
+            t = cbl(bp.sub("conv1"), y, 1, 1, 1, "relu")
+            t = splat(bp.sub("conv2"), t)
+            if stride > 1 or is_first:
+                t = F.avg_pool2d(t, 3, stride, 1)                                # avd, after the SplatConv (:318-319)
+            t = cbl(bp.sub("conv3"), t, 1)
+            short = y
+            if stride != 1 or inplanes != planes * 4:
+                short = F.avg_pool2d(short, stride, stride, 0)                   # avg_down :321-322
+                short = bn(bp.sub("batch_norm"), conv(bp.sub("conv4"), short))
+            y = bp.tap(F.relu(short + t))
+            inplanes = planes * 4
+    y = torch.flatten(F.adaptive_avg_pool2d(y, 1), 1)
+    return linear(p.sub("out"), y)
+
+
 FORWARD = {
+    "resnest50": lambda sd, x, **k: resnest(sd, x, (3, 4, 6, 3), **k),
+    "resnest101": lambda sd, x, **k: resnest(sd, x, (3, 4, 23, 3), **k),
     "resnet18": lambda sd, x, **k: resnet(sd, x, 18, **k),
     "resnet34": lambda sd, x, **k: resnet(sd, x, 34, **k),
     "resnet50": lambda sd, x, **k: resnet(sd, x, 50, **k),

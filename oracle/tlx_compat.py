@@ -106,6 +106,10 @@ class Module(torch.nn.Module):
 class Sequential(Module):
     def __init__(self, *layers):
         super().__init__()
+        if len(layers) == 1 and isinstance(layers[0], dict):     # OrderedDict of named layers (classification/resnest.py:479)
+            for k, l in layers[0].items():
+                self.add_module(str(k), l)
+            return
         if len(layers) == 1 and isinstance(layers[0], (list, tuple)):
             layers = tuple(layers[0])
         for i, l in enumerate(layers):
@@ -300,6 +304,36 @@ def concat(values, axis=0):
     return torch.cat(list(values), dim=axis)
 
 
+def split(value, num_or_size_splits, axis=0):
+    """classification/resnest.py:150-151,160-161: equal parts (int) or the given sizes along ``axis``."""
+    if isinstance(num_or_size_splits, int):
+        return list(torch.chunk(value, num_or_size_splits, dim=axis))
+    return list(torch.split(value, list(num_or_size_splits), dim=axis))
+
+
+def add_n(inputs):
+    out = inputs[0]
+    for t in inputs[1:]:
+        out = out + t
+    return out
+
+
+def multiply(x, y):
+    return torch.mul(x, y)
+
+
+def transpose(a, perm=None, conjugate=False):
+    return a.permute(*perm) if perm is not None else a.t()
+
+
+def softmax(logits, axis=-1):
+    return F.softmax(logits, dim=axis)
+
+
+def sigmoid(x):
+    return torch.sigmoid(x)
+
+
 class _Init:
     """Inert initializer: weights are injected by the harness."""
 
@@ -335,7 +369,8 @@ def _build_modules():
     nn.Conv2d = GroupConv2d
     nn.Layer = Module
     nn.initializers = init
-    for fn in (add, relu, reshape, flatten, squeeze, argmax, get_tensor_shape, concat):
+    for fn in (add, relu, reshape, flatten, squeeze, argmax, get_tensor_shape, concat, split, add_n, multiply, transpose, softmax,
+               sigmoid):
         setattr(tlx, fn.__name__, fn)
         setattr(ops, fn.__name__, fn)
     tlx.FlattenReshape = FlattenReshape

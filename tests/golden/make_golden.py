@@ -43,8 +43,9 @@ CASES = {
     "mobilenet_v1_det": (2, 96),
     "resnet50_vd": (1, 128),              # segmentation backbone: AvgPool2d shortcut, dilation 2 / 4; four stage outputs
     "resnet18_vd": (2, 96),
+    "resnest50": (2, 128),                # split attention (radix 2), avd / avg_down average pools, deep stem
 }
-MANIFEST_ONLY = ["resnet34", "resnet101", "wide_resnet50_2", "resnext50_64x4d"]
+MANIFEST_ONLY = ["resnet34", "resnet101", "wide_resnet50_2", "resnext50_64x4d", "resnest101"]
 
 # BASELINE.json configurations at their stated size: fixture file -> (model, n_images, image size, subsample).
 # Images are testing.structured_images (image i depends on (seed, i) only), so they are the FIRST n images of the full batch the GPU test feeds
@@ -65,7 +66,13 @@ def main():
     torch.set_num_threads(os.cpu_count() or 1)
     out_dir = os.path.dirname(os.path.abspath(__file__))
     manifests = {}
+    only = sys.argv[1:]                      # `make_golden.py resnest50 resnest101`: (re)mint these only, keep the rest
+    if only:
+        with open(os.path.join(out_dir, "manifests.json")) as f:
+            manifests = json.load(f)
     for name in list(CASES) + MANIFEST_ONLY:
+        if only and name not in only:
+            continue
         model = ref_loader.build(name)
         manifest = [(k, list(v.shape)) for k, v in model.state_dict().items()]
         manifests[name] = manifest
@@ -88,6 +95,8 @@ def main():
         )
         print(name, [tuple(o.shape) for o in outs], "std", float(outs[0].std()))
     for fname, (name, n, size, sub) in FULL_SIZE.items():
+        if only and fname not in only:
+            continue
         model = ref_loader.build(name)
         sd = seeded_state_dict(model.state_dict(), name)
         model.load_state_dict(sd)
@@ -110,6 +119,11 @@ def main():
             **arrays,
         )
         print(fname, [tuple(o.shape) for o in outs], "std", float(outs[0].std()))
+    with open(os.path.join(out_dir, "manifests.json"), "w") as f:
+        json.dump(manifests, f)
+    if only:
+        print("wrote", out_dir, only)
+        return
     # OpenCV INTER_LINEAR vectors for oracle/cv_resize.py (the arithmetic behind tensorlayerx's Resize on numpy images)
     import cv2
     rng = np.random.default_rng(0)

@@ -951,3 +951,68 @@ def test_resnet_vd_segmentation_backbone_vs_reference_golden(name, n, size):
     plan = next(iter(m.__dict__["_b200_plans"].values()))[0]
     kernels = [plan.op_info(i)["kernel"] for i in range(len(plan.spec.ops))]
     assert "avgpool_nhwc" in kernels
+
+
+@pytest.mark.gpu
+def test_resnest50_split_attention_vs_reference_golden():
+    """classification/resnest.py (resnest50: radix 2, deep stem, avd, avg_down): the radix-major grouped 3x3 as a dense conv,
+    GAP over all radix groups + the first attention conv with repeated filters, TLXCV_OP_SPLAT_APPLY (radix softmax x
+    multiply x sum), 3x3 / stride-2 / pad-1 and 2x2 / stride-2 average pools.  Golden = the reference's own file."""
+    outs, refs = _model_case("resnest50", 2, 128, "bf16", golden=True)
+    y, r = outs[0], refs[0]
+    err = float((y - r).abs().max())
+    top2 = r.topk(2, dim=1).values
+    assert err <= 1e-2, f"max-abs logit error {err:.3e} (logit std {float(r.std()):.3f})"
+    assert bool(((y.argmax(1) == r.argmax(1)) | ((top2[:, 0] - top2[:, 1]) <= 2 * err)).all())
+    outs, refs = _model_case("resnest50", 2, 96, "f32")
+    assert float((outs[0] - refs[0]).abs().max()) <= 1e-4
+    assert torch.equal(outs[0].argmax(1), refs[0].argmax(1))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,c,hw,radix,card", [(3, 64, 14, 2, 1), (2, 128, 9, 2, 4), (5, 32, 7, 4, 2), (1, 256, 28, 2, 1)])
+def test_split_attention_op_radix_and_cardinality(n, c, hw, radix, card):
+    """TLXCV_OP_SPLAT_APPLY against the reference's tensor algebra (rSoftmax resnest.py:64-82 + split / multiply / add_n
+    :159-162), including cardinality > 1 (the [cardinality][radix][C / cardinality] -> [radix][C] reordering of the logits)."""
+    import tlxcv_b200 as tlx
+    from tlxcv_b200 import graph as G, nn, runtime
+
+    class Net(nn.Module):
+        def forward(self, x, logits):
+            return G.active().splat_apply(x, logits, radix, card)
+
+    g = torch.Generator().manual_seed(n * 100 + c)
+    x = torch.randn(n, radix * c, hw, hw, generator=g)
+    logits = torch.randn(n, radix * c, 1, 1, generator=g) * 2
+    net = Net().cuda().set_eval()
+    for prec, tol in ((runtime.PREC_F32, 1e-5), (runtime.PREC_BF16, 3e-2)):
+        plan, _, flat = runtime.get_plan(net, (x.cuda(), logits.cuda()), {}, precision=prec)
+        out = plan.run(flat, graph=False)[0].cpu()
+        q = (lambda t: t) if prec == runtime.PREC_F32 else (lambda t: t.bfloat16().float())
+        att = q(logits).reshape(n, card, radix, -1).permute(0, 2, 1, 3)
+        att = torch.softmax(att, dim=1).reshape(n, -1, 1, 1)
+        want = sum(a * t for a, t in zip(torch.chunk(att, radix, 1), torch.chunk(q(x), radix, 1)))
+        assert out.shape == want.shape
+        assert float((out - want).abs().max()) <= tol * max(1.0, float(want.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("k,stride,pad,hw", [(3, 2, 1, 14), (3, 2, 1, 9), (3, 1, 1, 8), (2, 2, 0, 12)])
+def test_average_pool_with_padding(k, stride, pad, hw):
+    """nn.AvgPool2d(3, stride, padding=1) of ResNeSt's avd pool (resnest.py:245-250): zeros count in the mean (torch default)."""
+    from tlxcv_b200 import nn, runtime
+
+    class Net(nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.pool = nn.AvgPool2d(kernel_size=k, stride=stride, padding=pad, data_format="channels_first")
+
+        def forward(self, x):
+            return self.pool(x)
+
+    x = torch.randn(3, 24, hw, hw, generator=torch.Generator().manual_seed(k * 10 + hw))
+    net = Net().cuda().set_eval()
+    plan, _, flat = runtime.get_plan(net, (x.cuda(),), {}, precision=runtime.PREC_F32)
+    out = plan.run(flat, graph=False)[0].cpu()
+    want = F.avg_pool2d(x, k, stride, pad)
+    assert out.shape == want.shape and float((out - want).abs().max()) <= 1e-5

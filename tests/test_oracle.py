@@ -16,8 +16,8 @@ from tlxcv_b200.testing import (flatten_outputs, model_input, seeded_state_dict,
                                 synthetic_images)
 
 GOLDEN = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls", "darknet53_det",
-          "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnet18_vd"]
-CLASSIFIERS = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls"]
+          "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnet18_vd", "resnest50"]
+CLASSIFIERS = ["resnet50", "resnet18", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls", "resnest50"]
 # fixtures were minted with oneDNN on the build container's CPU; another CPU may pick other conv kernels
 ATOL = 2e-5
 
@@ -75,7 +75,8 @@ def test_restated_matches_full_size_golden(fname, golden_dir, manifests):
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")
 @pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d", "mobilenet_v2", "mobilenet_v1", "darknet53_cls",
-                                  "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnet18_vd"])
+                                  "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnet18_vd",
+                                  "resnest50"])
 def test_restated_matches_reference_files_live(name):
     """Bit-for-bit: the restatement and the reference's own file, same weights, same input."""
     torch.manual_seed(0)
@@ -94,7 +95,8 @@ def test_restated_matches_reference_files_live(name):
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")
 def test_reference_manifests_match_committed(manifests):
-    for name in ("resnet50", "mobilenet_v2", "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd"):
+    for name in ("resnet50", "mobilenet_v2", "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnest50",
+                 "resnest101"):
         model = ref_loader.build(name)
         assert [(k, tuple(v.shape)) for k, v in model.state_dict().items()] == manifests[name]
 

@@ -91,7 +91,8 @@ def test_predict_is_one_plan_with_argmax():
 
 @pytest.mark.skipif(not ref_loader.available(), reason="/root/reference is not mounted here")
 @pytest.mark.parametrize("name", ["resnet50", "resnext50_32x4d", "mobilenet_v1", "mobilenet_v2", "darknet53_cls",
-                                  "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnet18_vd"])
+                                  "darknet53_det", "yolov3_darknet53", "mobilenet_v1_det", "resnet50_vd", "resnet18_vd",
+                                  "resnest50"])
 def test_reference_files_run_unmodified_on_the_product_shim(name, manifests):
     """Drop-in: the reference's own model file, imported against tlxcv_b200 installed as `tensorlayerx`,
     builds B200-backed modules with the reference manifest and traces to the same plan as our model."""

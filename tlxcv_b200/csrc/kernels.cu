@@ -350,11 +350,12 @@ __global__ void maxpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
   Vec8<T>::store(dst + idx * 8, m);
 }
 
-// AvgPool2d(k, stride) without padding (the 2x2 / stride-2 pool in front of the shortcut conv of a ResNet_vd block,
-// segmentation/backbones/resnet_vd.py:25-27,45-46): fp32 sum of the window in (r, s) order, times 1 / k^2, one rounding
+// AvgPool2d(k, stride, pad) (the 2x2 / stride-2 pool in front of the shortcut conv of a ResNet_vd / ResNeSt block,
+// segmentation/backbones/resnet_vd.py:25-27,45-46; ResNeSt's 3x3 / stride-2 / pad-1 "avd" pool, classification/resnest.py:245-250):
+// fp32 sum of the window in (r, s) order, times 1 / k^2 (padding counts as zeros: torch's count_include_pad default), one rounding
 template <typename T>
 __global__ void avgpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int H, int W, int C8, int P, int Q, int k,
-                                    int stride, size_t total) {
+                                    int stride, int pad, size_t total) {
   pdl_wait();
   const size_t idx = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
@@ -367,8 +368,10 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
   float m[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   for (int r = 0; r < k; ++r)
     for (int s2 = 0; s2 < k; ++s2) {
+      const int h = pp * stride - pad + r, w = q * stride - pad + s2;
+      if (h < 0 || h >= H || w < 0 || w >= W) continue;
       float v[8];
-      Vec8<T>::load(src + ((n * H + pp * stride + r) * W + q * stride + s2) * static_cast<size_t>(C8) * 8 + c8 * 8, v);
+      Vec8<T>::load(src + ((n * H + h) * W + w) * static_cast<size_t>(C8) * 8 + c8 * 8, v);
 #pragma unroll
       for (int i = 0; i < 8; ++i) m[i] += v[i];
     }
@@ -378,13 +381,63 @@ __global__ void avgpool_nhwc_kernel(const T* __restrict__ src, T* __restrict__ d
   Vec8<T>::store(dst + idx * 8, m);
 }
 
+// Split attention (ResNeSt SplatConv, classification/resnest.py:53-82,146-166): x holds `radix` channel groups of C = G * cpc
+// channels ([r][g][j] order: `tlx.split(x, radix)`), att the attention logits of the block in the conv's [g][r][j] order
+// (rSoftmax reshapes them to (batch, G, radix, cpc), soft-maxes over radix and flattens to [r][g][j]):
+//   out[n, p, c] = sum_r softmax_r(att[n, g, :, j])[r] * x[n, p, r * C + c],   c = g * cpc + j
+// Block = (image, slice of the pixels): the radix x C probabilities are computed once into shared memory, then every
+// thread streams 8 channels of a pixel per step.
+__device__ __forceinline__ float to_float(float v) { return v; }
+__device__ __forceinline__ float to_float(__nv_bfloat16 v) { return __bfloat162float(v); }
+template <typename T>
+__global__ void splat_apply_kernel(const T* __restrict__ x, const T* __restrict__ att, T* __restrict__ dst, int HW, int C, int radix,
+                                   int cpc, int slices) {
+  extern __shared__ float prob[];  // [radix][C]
+  pdl_wait();
+  const int n = blockIdx.x / slices, slice = blockIdx.x % slices;
+  const T* a = att + static_cast<size_t>(n) * radix * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    const int g = c / cpc, j = c - g * cpc;
+    float mx = -3.402823466e38f;
+    for (int r = 0; r < radix; ++r) mx = fmaxf(mx, to_float(a[(g * radix + r) * cpc + j]));
+    float sum = 0.0f;
+    for (int r = 0; r < radix; ++r) {
+      const float e = expf(to_float(a[(g * radix + r) * cpc + j]) - mx);
+      prob[r * C + c] = e;
+      sum += e;
+    }
+    const float inv = 1.0f / sum;
+    for (int r = 0; r < radix; ++r) prob[r * C + c] *= inv;
+  }
+  __syncthreads();
+  const int C8 = C / 8;
+  const int per = (HW + slices - 1) / slices;
+  const int p0 = slice * per, p1 = min(HW, p0 + per);
+  const size_t total = static_cast<size_t>(p1 - p0) * C8;
+  for (size_t i = threadIdx.x; i < total; i += blockDim.x) {
+    const int c8 = static_cast<int>(i % C8);
+    const size_t pix = static_cast<size_t>(n) * HW + p0 + i / C8;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < radix; ++r) {
+      float v[8];
+      Vec8<T>::load(x + (pix * radix + r) * static_cast<size_t>(C) + c8 * 8, v);
+      const float* pr = prob + r * C + c8 * 8;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = fmaf(pr[k], v[k], acc[k]);
+    }
+    Vec8<T>::store(dst + pix * static_cast<size_t>(C) + c8 * 8, acc);
+  }
+}
+
 // global average pool: block per image, blockDim = (8-channel groups, kGapSlices pixel slices).  Each thread sums its
 // slice of the pixels in pixel order (fp32), the slices are then added in slice order through shared memory: four times
 // the loads in flight of a thread-per-group kernel, which was latency-bound (49 dependent-issue loads per thread).
-constexpr int kGapSlices = 4;
+// (blockDim.y = 4 slices for 2048 channels up to 32 for 128: narrow maps - the pooled radix groups of a ResNeSt block - would
+// otherwise leave most of the block idle)
 template <typename T>
 __global__ void gap_nhwc_kernel(const T* __restrict__ src, T* __restrict__ dst, int HW, int C8) {
-  extern __shared__ float gap_part[];  // [kGapSlices - 1][C8 * 8]
+  extern __shared__ float gap_part[];  // [slices - 1][C8 * 8]
+  const int kGapSlices = blockDim.y;
   pdl_wait();
   const int n = blockIdx.x;
   const T* s = src + static_cast<size_t>(n) * HW * C8 * 8;
@@ -877,22 +930,40 @@ cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C,
   return cudaGetLastError();
 }
 
-cudaError_t avgpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int is_f32,
+cudaError_t splat_apply(const void* x, const void* att, void* dst, int N, int HW, int C, int radix, int cardinality, int is_f32,
+                        cudaStream_t st) {
+  if (C % 8 || radix < 1 || cardinality < 1 || C % cardinality) return cudaErrorInvalidValue;
+  // enough blocks to fill the chip: images x pixel slices
+  int slices = 1;
+  while (N * slices < 2 * 148 && slices * 64 < HW) slices *= 2;
+  const size_t smem = static_cast<size_t>(radix) * C * sizeof(float);
+  if (is_f32)
+    TLXCV_LAUNCH(splat_apply_kernel<float>, N * slices, kThreads, smem, st, static_cast<const float*>(x), static_cast<const float*>(att),
+                 static_cast<float*>(dst), HW, C, radix, C / cardinality, slices);
+  else
+    TLXCV_LAUNCH(splat_apply_kernel<__nv_bfloat16>, N * slices, kThreads, smem, st, static_cast<const __nv_bfloat16*>(x),
+                 static_cast<const __nv_bfloat16*>(att), static_cast<__nv_bfloat16*>(dst), HW, C, radix, C / cardinality, slices);
+  return cudaSuccess;
+}
+
+cudaError_t avgpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, int is_f32,
                          cudaStream_t st) {
-  if (C % 8 || (P - 1) * stride + k > H || (Q - 1) * stride + k > W) return cudaErrorInvalidValue;
+  if (C % 8 || pad < 0 || (P - 1) * stride + k > H + 2 * pad || (Q - 1) * stride + k > W + 2 * pad) return cudaErrorInvalidValue;
   const size_t total = static_cast<size_t>(N) * P * Q * (C / 8);
   if (is_f32)
-    TLXCV_LAUNCH(avgpool_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, total);
+    TLXCV_LAUNCH(avgpool_nhwc_kernel<float>, blocks_for(total), kThreads, 0, st, static_cast<const float*>(src), static_cast<float*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   else
-    TLXCV_LAUNCH(avgpool_nhwc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, total);
+    TLXCV_LAUNCH(avgpool_nhwc_kernel<__nv_bfloat16>, blocks_for(total), kThreads, 0, st, static_cast<const __nv_bfloat16*>(src), static_cast<__nv_bfloat16*>(dst), H, W, C / 8, P, Q, k, stride, pad, total);
   return cudaGetLastError();
 }
 
 cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st) {
   if (C % 8) return cudaErrorInvalidValue;
-  const int tx = C / 8 >= 256 ? 256 : (C / 8 >= 128 ? 128 : 64);
-  const dim3 threads(tx, kGapSlices);
-  const int smem = (kGapSlices - 1) * C * static_cast<int>(sizeof(float));
+  int tx = 16;
+  while (tx < C / 8 && tx < 256) tx *= 2;
+  const int slices = std::max(4, std::min(32, 1024 / tx));
+  const dim3 threads(tx, slices);
+  const int smem = (slices - 1) * C * static_cast<int>(sizeof(float));
   if (smem > 48 * 1024) return cudaErrorInvalidValue;  // C > 4096: not a shape of this path
   if (is_f32)
     TLXCV_LAUNCH(gap_nhwc_kernel<float>, N, threads, smem, st, static_cast<const float*>(src), static_cast<float*>(dst), HW, C / 8);

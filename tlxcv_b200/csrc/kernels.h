@@ -220,7 +220,9 @@ cudaError_t import_u8_resize(const uint8_t* src, void* dst, const float* mean, c
 cudaError_t maxpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad,
                          int is_f32, cudaStream_t st);
 // AvgPool2d(k, stride), no padding (windows inside the map)
-cudaError_t avgpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int is_f32,
+cudaError_t splat_apply(const void* x, const void* att, void* dst, int N, int HW, int C, int radix, int cardinality, int is_f32,
+                        cudaStream_t st);
+cudaError_t avgpool_nhwc(const void* src, void* dst, int N, int H, int W, int C, int P, int Q, int k, int stride, int pad, int is_f32,
                          cudaStream_t st);
 cudaError_t gap_nhwc(const void* src, void* dst, int N, int HW, int C, int is_f32, cudaStream_t st);
 cudaError_t dwconv_nhwc(const void* src, const void* w_rsc, void* dst, const float* scale, const float* shift,

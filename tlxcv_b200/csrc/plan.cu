@@ -32,7 +32,7 @@ struct TensorRt {
 };
 
 enum Impl : int { kImplImport, kImplExport, kImplTcConv, kImplDwConv, kImplDirectF32, kImplMaxpool, kImplGap, kImplAddAct, kImplArgmax,
-                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat, kImplSoftmax, kImplSoftmaxCe, kImplAvgpool };
+                  kImplStem, kImplSlab, kImplNop, kImplImportU8, kImplUpsampleConcat, kImplSoftmax, kImplSoftmaxCe, kImplAvgpool, kImplSplatApply };
 
 struct OpRt {
   tlxcv_op_desc d;
@@ -590,7 +590,10 @@ int launch_op(tlxcv_plan* p, OpRt& op, const void* const* inputs, void* const* o
       TLX_CUDA(ctx, maxpool_nhwc(pin, pout, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, d.r, d.stride, d.pad, is_f32, st));
       break;
     case kImplAvgpool:
-      TLX_CUDA(ctx, avgpool_nhwc(pin, pout, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, d.r, d.stride, is_f32, st));
+      TLX_CUDA(ctx, avgpool_nhwc(pin, pout, in.d.n, in.d.h, in.d.w, in.d.c, out.d.h, out.d.w, d.r, d.stride, d.pad, is_f32, st));
+      break;
+    case kImplSplatApply:
+      TLX_CUDA(ctx, splat_apply(pin, pres, pout, in.d.n, in.d.h * in.d.w, out.d.c, d.r, d.groups, is_f32, st));
       break;
     case kImplGap:
       TLX_CUDA(ctx, gap_nhwc(pin, pout, in.d.n, in.d.h * in.d.w, in.d.c, is_f32, st));
@@ -1060,13 +1063,25 @@ int tlxcv_plan_build(tlxcv_ctx* ctx, const tlxcv_tensor_desc* tensors, int n_ten
         set_info(op, "maxpool_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
       case TLXCV_OP_AVGPOOL:
-        if (d.r != d.s || d.pad != 0 || d.r < 1 || d.stride < 1)
-          return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: average pooling needs a square window without padding", i);
-        if (o.d.h != (in.d.h - d.r) / d.stride + 1 || o.d.w != (in.d.w - d.r) / d.stride + 1 || o.d.c != in.d.c || in.cs != in.d.c)
+        if (d.r != d.s || d.pad < 0 || 2 * d.pad >= d.r + 1 || d.r < 1 || d.stride < 1)
+          return fail(ctx, TLXCV_ERR_UNSUPPORTED, "op %d: average pooling needs a square window with padding below half of it", i);
+        if (o.d.h != (in.d.h + 2 * d.pad - d.r) / d.stride + 1 || o.d.w != (in.d.w + 2 * d.pad - d.r) / d.stride + 1 || o.d.c != in.d.c ||
+            in.cs != in.d.c)
           return fail(ctx, TLXCV_ERR_INVALID, "op %d: avgpool output shape mismatch", i);
         op.impl = kImplAvgpool;
         set_info(op, "avgpool_nhwc", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
         break;
+      case TLXCV_OP_SPLAT_APPLY: {
+        if (d.in1 < 0 || d.r < 1 || d.groups < 1) return fail(ctx, TLXCV_ERR_INVALID, "op %d: split attention needs logits, radix and cardinality", i);
+        const TensorRt& lg = p->tensors[d.in1];
+        if (in.d.c != d.r * o.d.c || lg.d.c != in.d.c || lg.d.h != 1 || lg.d.w != 1 || lg.d.n != in.d.n || o.d.h != in.d.h || o.d.w != in.d.w ||
+            o.d.n != in.d.n || o.d.c % 8 || o.d.c % d.groups || in.cs != in.d.c || lg.cs != lg.d.c)
+          return fail(ctx, TLXCV_ERR_INVALID, "op %d: split attention shape mismatch", i);
+        if (lg.d.dtype != in.d.dtype) return fail(ctx, TLXCV_ERR_INVALID, "op %d: split attention operands differ in type", i);
+        op.impl = kImplSplatApply;
+        set_info(op, "splat_apply", 1, 0, 0, in_bytes + out_bytes, 0, 256, 0, 0);
+        break;
+      }
       case TLXCV_OP_GAP:
         if (o.d.h != 1 || o.d.w != 1 || o.d.c != in.d.c) return fail(ctx, TLXCV_ERR_INVALID, "op %d: gap output shape mismatch", i);
         op.impl = kImplGap;

@@ -120,17 +120,30 @@ class Graph:
         return out
 
     # -- ops ----------------------------------------------------------------
-    def conv(self, x, layer) -> SymTensor:
+    def conv(self, x, layer, dup_in=1) -> SymTensor:
+        """``dup_in`` > 1: the input holds ``dup_in`` channel groups that the reference sums before the conv
+        (``add_n(split(x, radix))`` in front of SplatConv's 1x1 conv): the planner tiles the filters along C_in instead."""
         n, c, h, w = _nchw(x, "GroupConv2d")
         kout, cg, r, s = layer.filters.shape
         g = layer.n_group
-        if c != cg * g:
-            raise ValueError(f"GroupConv2d {'.'.join(self._path)}: input has {c} channels, filters expect {cg * g}")
+        if c != cg * g * dup_in:
+            raise ValueError(f"GroupConv2d {'.'.join(self._path)}: input has {c} channels, filters expect {cg * g * dup_in}")
+        if dup_in > 1 and (g != 1 or (r, s) != (1, 1)):
+            raise NotImplementedError("summed channel groups in front of a conv: 1x1 dense convs only")
         (sh, sw), (ph, pw), (dh, dw) = layer.stride, layer.padding, layer.dilation
         p = (h + 2 * ph - dh * (r - 1) - 1) // sh + 1
         q = (w + 2 * pw - dw * (s - 1) - 1) // sw + 1
-        attrs = dict(r=r, s=s, stride=(sh, sw), pad=(ph, pw), dil=(dh, dw), groups=g)
+        attrs = dict(r=r, s=s, stride=(sh, sw), pad=(ph, pw), dil=(dh, dw), groups=g, dup_in=dup_in)
         return self._emit("conv", [x], (n, kout, p, q), attrs, layer)
+
+    def splat_apply(self, x, logits, radix, cardinality) -> SymTensor:
+        """Split attention of ResNeSt (classification/resnest.py:53-82,160-166): softmax over the radix axis of ``logits``
+        ((N, radix*C, 1, 1), the conv's [cardinality][radix][C/cardinality] order), times the radix channel groups of
+        ``x`` ((N, radix*C, H, W)), summed."""
+        n, c, h, w = _nchw(x, "SplatConv")
+        if tuple(logits.shape) != (n, c, 1, 1) or c % radix or (c // radix) % cardinality:
+            raise ValueError(f"split attention: map {x.shape}, logits {logits.shape}, radix {radix}, cardinality {cardinality}")
+        return self._emit("splat_apply", [x, logits], (n, c // radix, h, w), dict(radix=radix, cardinality=cardinality))
 
     def normalize_u8(self, x, layer) -> SymTensor:
         """uint8 NHWC image batch -> logical (N, C, H, W) activation, (x - mean) / std per channel."""
@@ -201,11 +214,14 @@ class Graph:
     def avgpool(self, x, k, stride, pad) -> SymTensor:
         n, c, h, w = _nchw(x, "AvgPool2d")
         (kh, kw), (sh, sw), (ph, pw) = k, stride, pad
-        if (ph, pw) != (0, 0) or kh != kw or sh != sw:
-            raise NotImplementedError("AvgPool2d: only square windows without padding are on the hot path")
-        if (h - kh) % sh or (w - kw) % sw:
+        if ph != pw or kh != kw or sh != sw or 2 * ph > kh:
+            raise NotImplementedError("AvgPool2d: only square windows with symmetric padding are on the hot path")
+        if ph == 0 and ((h - kh) % sh or (w - kw) % sw):
             raise NotImplementedError(f"AvgPool2d({kh}, {sh}) on a {h}x{w} map: windows must tile the map exactly")
-        return self._emit("avgpool", [x], (n, c, (h - kh) // sh + 1, (w - kw) // sw + 1), dict(k=(kh, kw), stride=(sh, sw)))
+        if (kh, sh, ph) == (1, 1, 0):
+            return x                # AvgPool2d(1, 1): ResNeSt's avg_down shortcut of a stride-1 block (classification/resnest.py:263-269)
+        return self._emit("avgpool", [x], (n, c, (h + 2 * ph - kh) // sh + 1, (w + 2 * pw - kw) // sw + 1),
+                          dict(k=(kh, kw), stride=(sh, sw), pad=(ph, pw)))
 
     def gap(self, x) -> SymTensor:
         n, c, h, w = _nchw(x, "AdaptiveAvgPool2d")

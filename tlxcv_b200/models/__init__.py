@@ -15,6 +15,7 @@ from .darknet import DarkNet  # noqa: F401
 from .det_mobilenet import MobileNet  # noqa: F401
 from .yolov3 import YOLOv3, YOLOv3FPN, YOLOv3Head, YoloDetBlock  # noqa: F401
 from .resnet_vd import ResNet_vd  # noqa: F401
+from .resnest import ResNeSt, resnest50, resnest101  # noqa: F401
 
 # name -> constructor, keyed like tlxcv_b200.testing.RECIPES / tests/golden
 REGISTRY = {
@@ -25,5 +26,6 @@ REGISTRY = {
     "mobilenet_v1": MobileNetV1, "mobilenet_v2": mobilenet_v2,
     "darknet53_cls": darknet53, "darknet53_det": DarkNet,
     "mobilenet_v1_det": MobileNet, "yolov3_darknet53": YOLOv3,
+    "resnest50": resnest50, "resnest101": resnest101,
     "resnet50_vd": ResNet_vd, "resnet18_vd": lambda **kw: ResNet_vd(layers=18, **kw),
 }

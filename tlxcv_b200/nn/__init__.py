@@ -89,14 +89,18 @@ class Module(torch.nn.Module):
     def __call__(self, *args, **kwargs):
         g = _g.active()
         if g is not None:
+            # a ResNeSt SplatConv (the reference's own class included) is lowered as ONE unit: its forward is tensor algebra
+            # (split / add_n / reshape / transpose / softmax / multiply, classification/resnest.py:146-166) that the plan
+            # runs as GAP + two 1x1 convs + one split-attention pass
+            fwd = (lambda x: split_attention(self, x)) if _is_splat_conv(self) else self.forward
             name = g.names.get(id(self)) if hasattr(g, "names") else None
             if name:
                 saved, g._path = g._path, [name]
                 try:
-                    return self.forward(*args, **kwargs)
+                    return fwd(*args, **kwargs)
                 finally:
                     g._path = saved
-            return self.forward(*args, **kwargs)
+            return fwd(*args, **kwargs)
         from .. import runtime
         return runtime.run_module(self, args, kwargs)
 
@@ -240,11 +244,49 @@ def _sym(x, who):
     return x
 
 
+def _is_splat_conv(m):
+    """Structural test for ResNeSt's split-attention conv (classification/resnest.py:84-143)."""
+    return (type(m).__name__ == "SplatConv" and
+            all(hasattr(m, a) for a in ("radix", "conv1", "conv2", "conv3", "rsoftmax", "avg_pool2d")))
+
+
+def split_attention(m, x):
+    """``SplatConv.forward`` (classification/resnest.py:146-166) on the plan.
+
+    ``y = conv1(x)`` holds ``radix`` channel groups; the reference sums them, pools globally, runs ``conv2`` (+BN+ReLU) and
+    ``conv3``, soft-maxes over the radix axis and returns the attention-weighted sum of the groups.  Here the global pool runs
+    over all groups at once and the sum moves into ``conv2`` (filters repeated along C_in: mean and sum commute with the
+    1x1 conv), then ONE pass does softmax x multiply x sum (``TLXCV_OP_SPLAT_APPLY``)."""
+    g = _g.active()
+    x = _sym(x, "SplatConv")
+    radix = int(m.radix)
+    if radix < 2:
+        raise NotImplementedError("SplatConv with radix 1 gates with a sigmoid (resnest.py:78-79): not on the B200 path")
+    y = m.conv1(x)
+    pooled = g.gap(y)
+    conv2 = [c for c in m.conv2.children() if isinstance(c, GroupConv2d)]
+    bn2 = [c for c in m.conv2.children() if isinstance(c, BatchNorm)]
+    if len(conv2) != 1 or len(bn2) != 1:
+        raise NotImplementedError("SplatConv.conv2 must be one GroupConv2d followed by one BatchNorm")
+    names = getattr(g, "names", {})
+    saved, g._path = g._path, [names.get(id(conv2[0])) or ".".join(g._path)]
+    try:
+        h = conv2[0]._apply_act(g.conv(pooled, conv2[0], dup_in=radix))
+    finally:
+        g._path = saved
+    logits = m.conv3(bn2[0](h))
+    return g.splat_apply(y, logits, radix, int(m.rsoftmax.cardinality))
+
+
 class Sequential(Module):
     """``nn.Sequential([l0, l1])`` and ``nn.Sequential(l0, l1)`` (resnet.py:247,284; ops_fusion.py:48)."""
 
     def __init__(self, *layers, name=None):
         super().__init__(name)
+        if len(layers) == 1 and isinstance(layers[0], dict):     # OrderedDict of named layers (classification/resnest.py:479)
+            for key, layer in layers[0].items():
+                self.add_module(str(key), layer)
+            return
         if len(layers) == 1 and isinstance(layers[0], (list, tuple)):
             layers = tuple(layers[0])
         for i, layer in enumerate(layers):

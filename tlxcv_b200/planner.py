@@ -23,7 +23,7 @@ from . import graph as _g
 
 # op kinds / activations / dtypes: keep in sync with include/tlxcv_b200.h
 (OP_IMPORT_NCHW, OP_CONV, OP_MAXPOOL, OP_GAP, OP_LINEAR, OP_ADD_ACT, OP_ARGMAX, OP_EXPORT_NCHW, OP_IMPORT_U8,
- OP_UPSAMPLE_CONCAT, OP_SOFTMAX, OP_SOFTMAX_CE, OP_AVGPOOL) = range(13)
+ OP_UPSAMPLE_CONCAT, OP_SOFTMAX, OP_SOFTMAX_CE, OP_AVGPOOL, OP_SPLAT_APPLY) = range(14)
 ACT_NONE, ACT_RELU, ACT_RELU6, ACT_LEAKY = range(4)
 DT_U8 = 4
 DT_F32, DT_BF16, DT_I64, DT_ACT = 0, 1, 2, 3          # DT_ACT: bf16 in the default mode, f32 in validation mode
@@ -31,7 +31,39 @@ ROLE_INTERNAL, ROLE_INPUT, ROLE_OUTPUT = 0, 1, 2
 
 _ACT = {None: ACT_NONE, "relu": ACT_RELU, "relu6": ACT_RELU6, "leaky": ACT_LEAKY}
 OP_NAMES = ["import_nchw", "conv", "maxpool", "gap", "linear", "add_act", "argmax", "export_nchw", "import_u8_nhwc",
-            "upsample_concat", "softmax", "softmax_ce", "avgpool"]
+            "upsample_concat", "softmax", "softmax_ce", "avgpool", "splat_apply"]
+
+
+class DerivedConv:
+    """A conv whose packed filters are a FUNCTION of a module's filters, evaluated when the plan is built:
+
+    * ``kind="dense"``: a grouped conv with C_in != C_out (ResNeSt's radix-major 3x3, groups = cardinality * radix,
+      classification/resnest.py:103-112) as the dense conv with block-diagonal filters (zeros contribute exactly nothing);
+    * ``kind="tile"``: a 1x1 conv applied to the SUM of ``n`` channel groups of its input (``add_n(split(x, radix))`` ->
+      GAP -> conv, resnest.py:148-155) as one conv over all groups with the filters repeated along C_in.
+
+    The cache fingerprint follows the source module's parameters (``_parameters`` is the same dict)."""
+
+    def __init__(self, src, kind, n):
+        self.src, self.kind, self.n = src, kind, n
+        self._parameters, self._buffers = src._parameters, {}
+
+    @property
+    def filters(self):
+        w = self.src.filters.detach()
+        if self.kind == "tile":
+            return w.repeat(1, self.n, 1, 1).contiguous()
+        g = self.n
+        kout, cg, r, s = w.shape
+        dense = w.new_zeros((kout, cg * g, r, s))
+        per = kout // g
+        for i in range(g):
+            dense[i * per:(i + 1) * per, i * cg:(i + 1) * cg] = w[i * per:(i + 1) * per]
+        return dense
+
+    @property
+    def biases(self):
+        return self.src.biases
 
 
 @dataclass
@@ -168,6 +200,12 @@ def lower(graph: _g.Graph) -> PlanSpec:
             op = OpSpec(OP_CONV, ins[0], -1, r=a["r"], s=a["s"], stride=_square(a["stride"], "stride", nd.path),
                         pad=_square(a["pad"], "padding", nd.path), dil=_square(a["dil"], "dilation", nd.path),
                         groups=a["groups"], conv=nd.module, path=nd.path)
+            kout, cg = nd.module.filters.shape[:2]
+            if a.get("dup_in", 1) > 1:
+                op.conv = DerivedConv(nd.module, "tile", a["dup_in"])
+            elif op.groups > 1 and not (kout == cg * op.groups and (cg == 1 or (64 % cg == 0 and kout % 64 == 0))):
+                # only depthwise and C_in == C_out groups of 2..64 channels have grouped kernels: anything else runs dense
+                op.conv, op.groups = DerivedConv(nd.module, "dense", op.groups), 1
             cur, last = nd.out, i
             j = sole_consumer(cur, "bn")
             if j is not None:
@@ -274,7 +312,11 @@ def lower(graph: _g.Graph) -> PlanSpec:
         elif nd.op == "avgpool":
             a = nd.attrs
             out = new_tensor(graph.shapes[nd.out], DT_ACT)
-            spec.ops.append(OpSpec(OP_AVGPOOL, ins[0], out, r=a["k"][0], s=a["k"][1], stride=a["stride"][0], pad=0,
+            spec.ops.append(OpSpec(OP_AVGPOOL, ins[0], out, r=a["k"][0], s=a["k"][1], stride=a["stride"][0],
+                                   pad=a.get("pad", (0, 0))[0], path=nd.path))
+        elif nd.op == "splat_apply":
+            out = new_tensor(graph.shapes[nd.out], DT_ACT)
+            spec.ops.append(OpSpec(OP_SPLAT_APPLY, ins[0], out, in1=ins[1], r=nd.attrs["radix"], groups=nd.attrs["cardinality"],
                                    path=nd.path))
         elif nd.op == "gap":
             out = new_tensor(graph.shapes[nd.out], DT_ACT)

@@ -32,6 +32,7 @@ _DAMP = {
     "darknet53_cls": [r"_basic_block_\d+\._conv2\._bn\.gamma$"],
     "darknet53_det": [r"\.conv2\.batch_norm\.gamma$"],
     "resnet_vd_bottleneck": [r"\.conv2\.batch_norm\.gamma$"],
+    "resnest": [r"_bottleneck_\d+\.conv3\.batch_norm\.gamma$"],
     "resnet_vd_basic": [r"stage_list\.\d+\.\d+\.conv1\.batch_norm\.gamma$"],
 }
 
@@ -53,6 +54,8 @@ RECIPES = {
     "darknet53_det": ("darknet53_det", 1.0),
     "yolov3_darknet53": ("darknet53_det", 1.0),
     "mobilenet_v1_det": ("mobilenet_v1", 1.0),
+    "resnest50": ("resnest", 0.07),
+    "resnest101": ("resnest", 0.07),
     "resnet50_vd": ("resnet_vd_bottleneck", 1.0),
     "resnet18_vd": ("resnet_vd_basic", 1.0),
 }
