@@ -17,3 +17,4 @@ prof darknet53_cls 256 224
 prof resnet18 256 224
 prof yolov3_darknet53 64 608
 prof mobilenet_v1_det 256 300
+prof resnest50 256 224
