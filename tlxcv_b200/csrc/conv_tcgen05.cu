@@ -227,6 +227,18 @@ struct EpiArgs {
   const float* sc1_cache;                                 // smem [scale1(N1) | shift1(N1)]
 };
 
+// epilogue-warp barrier wait: with TLXCV_LANE0_POLL one lane polls and the warp re-converges (8 polling threads per CTA
+// instead of 256); otherwise every lane polls
+__device__ __forceinline__ void epi_wait(uint32_t bar, uint32_t parity, int lane) {
+#ifdef TLXCV_LANE0_POLL
+  if (lane == 0) mbar_wait(bar, parity);
+  __syncwarp();
+#else
+  (void)lane;
+  mbar_wait(bar, parity);
+#endif
+}
+
 template <int ACT>
 __device__ __forceinline__ float act1f(float v, float alpha) {
   if (ACT == TLXCV_ACT_RELU) return fmaxf(v, 0.0f);
@@ -356,7 +368,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
     const float4 sc_pf = sc_nx, sh_pf = sh_nx, sc2_pf = sc2_nx, sh2_pf = sh2_nx;
     if (sc_lane && unit + 1 < n_units) fetch_sc(n_tile + dn >= a.n_tiles ? n_tile + dn - a.n_tiles : n_tile + dn);
     if (btracer) trace_c(a.trace, 2, tr);  // [5k+1] tile set-up done
-    mbar_wait(a.tmem_full_bar + acc * 8, acc_phase);
+    epi_wait(a.tmem_full_bar + acc * 8, acc_phase, lane);
     tcgen05_fence_after();
     if (btracer) trace_c(a.trace, 2, tr);  // [5k+2] accumulator complete
     if (tracer) trace_c(a.trace, 2, tr);  // [3k+1] accumulator complete
@@ -416,7 +428,7 @@ __device__ __forceinline__ void epilogue_loop(const EpiArgs& a, int lg, int cgro
           asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           pf_issue();
         }
-        if (hh == 0 && !(a.ablate & 16)) mbar_wait(a.res_bar + slot * 8, (it / kSlots) & 1);  // residual item has landed in the ring slot
+        if (hh == 0 && !(a.ablate & 16)) epi_wait(a.res_bar + slot * 8, (it / kSlots) & 1, lane);  // residual item has landed in the ring slot
       } else if (!F32 && hh == 0) {
         // the TMA store that used this slot kSlots items ago must have finished reading it
         if (lane == 0) {
@@ -1069,10 +1081,10 @@ __device__ __forceinline__ void chain_e1(const EpiArgs& a, int lg, int cgroup, i
   constexpr int kChunks = N1 / 32;            // 32-channel chunks of acc1
   constexpr int kCpw1 = kChunks / 2;          // per warp (two column groups)
   const uint32_t b = tile_i & 1u;
-  mbar_wait(a.acc1_full_bar + b * 8, (tile_i >> 1) & 1u);
+  epi_wait(a.acc1_full_bar + b * 8, (tile_i >> 1) & 1u, lane);
   tcgen05_fence_after();
   // the second GEMM of the previous tile has finished reading A2 (first tile: passes at once)
-  mbar_wait(a.a2_empty_bar, (tile_i & 1u) ^ 1u);
+  epi_wait(a.a2_empty_bar, (tile_i & 1u) ^ 1u, lane);
   const int row = lg * 32 + lane;
   const uint32_t row_base = a.a2_smem + static_cast<uint32_t>(row) * 128u;
   const uint32_t swz = static_cast<uint32_t>(row & 7);
