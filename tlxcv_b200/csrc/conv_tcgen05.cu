@@ -641,9 +641,15 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
   extern __shared__ __align__(1024) uint8_t smem[];
   if ((smem_u32(smem) & 1023u) != 0) __trap();
   const int n_stages = p.stages, ring = p.ring;
+  // K blocks per pipeline slot.  A barrier round (wait, expect_tx / poll, fence, election, commit) costs the producer and
+  // the MMA warp ~300-400 cycles whatever it carries, and a 64-wide K block is 128 tensor-pipe cycles: 64-wide tiles with
+  // a K loop put TWO K blocks behind one full / empty barrier pair (ResNeXt 512-channel grouped 3x3, bs256: 42 of its 81 us
+  // were this skeleton with loads, MMAs and epilogue math all ablated)
+  const int kgroup = (!TWO && !DUAL && MODE != kModeGatherC4 && p.kgroup == 2) ? 2 : 1;
+  const int slot_b = kStageB * kgroup;
   const int epi_warps = p.epi_warps;
   const int staging_bytes = epi_warps * ring * 2048;
-  uint8_t* staging = smem + n_stages * kStageB;
+  uint8_t* staging = smem + n_stages * slot_b;
   float* sc_cache = reinterpret_cast<float*>(staging + staging_bytes);  // [BLOCK_N scale | 256: BLOCK_N shift]
   uint64_t* bars = reinterpret_cast<uint64_t*>(staging + staging_bytes + p.sc_bufs * kScaleBufBytes);
   uint64_t* full_bar = bars;                       // [kStages]  operands landed
@@ -724,6 +730,41 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const int c_base = p.a_chan_from_n ? n_tile * BLOCK_N : 0;
         // no divisions in the K loop: this single thread's per-iteration latency bounds small-N tiles
         int r = 0, sx = 0, cb = 0;
+        if (kgroup == 2) {  // two K blocks per slot (plain 64-wide tiles): one wait and one expect_tx per pair
+          for (int kb0 = 0; kb0 < p.num_kb; kb0 += 2) {
+            const int nk = min(2, p.num_kb - kb0);
+            mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
+            const uint32_t bar = smem_u32(&full_bar[ps.stage]);
+            if (p.ablate & 8) {  // timing experiment: operands never loaded
+              mbar_arrive(bar);
+              ps.advance(n_stages);
+              continue;
+            }
+            mbar_arrive_expect_tx(bar, nk * C::kStageBytes);
+            for (int j = 0; j < nk; ++j) {
+              const int kb = kb0 + j;
+              const uint32_t a_dst = smem_u32(smem + ps.stage * slot_b + j * kStageB);
+              if (MODE == kModeTiled) {
+                tma_load_2d(a_dst, &tmapA, bar, kb * KB, m0);
+              } else if (KB == kBlockK && p.pair_taps != 0) {
+                const uint32_t e = p.pair_taps >> (4 * kb);
+                tma_load_im2col_4d(a_dst, (e & 1) ? &tmapA2 : &tmapA, bar, 0, base_w, base_h, img, static_cast<uint16_t>((e >> 1) & 1),
+                                   static_cast<uint16_t>((e >> 2) & 1));
+              } else {
+                tma_load_im2col_4d(a_dst, &tmapA, bar, c_base + cb * KB, base_w, base_h, img,
+                                   static_cast<uint16_t>(sx * p.dil), static_cast<uint16_t>(r * p.dil));
+                if (++cb == p.kb_per_tap) {
+                  cb = 0;
+                  if (++sx == p.S) sx = 0, ++r;
+                }
+              }
+              tma_load_2d(a_dst + kAB, &tmapB, bar, kb * KB, n0);
+            }
+            ps.advance(n_stages);
+          }
+          if (!(p.ablate & 512)) trace_c(p.trace, 0, tr);  // [2k+1] all loads of the tile issued
+          continue;
+        }
         for (int kb = 0; kb < p.num_kb; ++kb) {
 #ifdef TLXCV_FINE_TRACE
           if (p.ablate & 512) trace_c(p.trace, 0, tr);  // round trace: before the empty wait
@@ -733,7 +774,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
           if (p.ablate & 512) trace_c(p.trace, 0, tr);  // round trace: slot free
 #endif
           const uint32_t bar = smem_u32(&full_bar[ps.stage]);
-          const uint32_t a_dst = smem_u32(smem + ps.stage * kStageB);
+          const uint32_t a_dst = smem_u32(smem + ps.stage * slot_b);
           if constexpr (TWO) {
             // both CTAs' bytes are counted on the LEADER's full barrier, which alone is armed (for both halves)
             const uint32_t lbar = mapa_u32(bar, 0);
@@ -827,10 +868,45 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         tcgen05_fence_after();
         if (tracer1) trace_c(p.trace, 1, tr);  // [4k+1] accumulator free
         const uint32_t tmem_d1 = tmem_base + acc * kAccCols;
+        if (kgroup == 2) {  // two K blocks per slot: one wait, one election, one commit per pair
+          auto issue_pair_kb = [&](int kk, uint32_t a_lo) {
+            const uint32_t b_lo = a_lo + (kAB >> 4);
+            if (!no_mma) {
+#pragma unroll
+              for (int k = 0; k < KB / 16; ++k) {
+                if (k == 0)
+                  umma_bf16_lohi<TWO>(tmem_d1, a_lo, b_lo, desc_hi, idesc, kk != 0);
+                else
+                  umma_bf16_lohi<TWO>(tmem_d1, a_lo + 2 * k, b_lo + 2 * k, desc_hi, idesc, 1);
+              }
+            }
+          };
+          for (int kb = 0; kb < num_kb; kb += 2) {
+            const uint32_t st = ps.stage;
+            mbar_wait(full0 + st * 8, ps.phase);
+            ps.advance(n_stages);
+            tcgen05_fence_after();
+            if (kb == 0 && tracer1) trace_c(p.trace, 1, tr);  // [4k+2] first operands landed
+            const uint32_t a_lo = smem_lo + st * (static_cast<uint32_t>(slot_b) >> 4);
+            if (kb + 1 < num_kb) {  // warp-uniform branch outside the election
+              if (elect_one_sync()) {
+                issue_pair_kb(kb, a_lo);
+                issue_pair_kb(kb + 1, a_lo + (kStageB >> 4));
+                umma_commit(empty0 + st * 8);
+              }
+            } else {
+              if (elect_one_sync()) {
+                issue_pair_kb(kb, a_lo);
+                umma_commit(empty0 + st * 8);
+              }
+            }
+            __syncwarp();
+          }
+        }
         // Up to two K blocks per round: this warp shares its scheduler with two epilogue warps, and the fixed cost of a round
         // (barrier poll, fence, election, uniform-register setup, commit) otherwise exceeds the 256 tensor-core cycles
         // of a 128-wide K block.
-        for (int kb = 0; kb < num_kb;) {
+        for (int kb = kgroup == 2 ? num_kb : 0; kb < num_kb;) {
           const uint32_t st0 = ps.stage;
 #ifdef TLXCV_FINE_TRACE
           if (rtracer) trace_c(p.trace, 1, tr);  // round trace: before the full wait
@@ -854,7 +930,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
             const bool second = DUAL && kk >= num_kb1;
             const uint32_t tmem_d = second ? tmem_d1 + BLOCK_N : tmem_d1;
             const int kbl = second ? kk - num_kb1 : kk;  // first K block of an accumulator overwrites it
-            const uint32_t a_lo = smem_lo + st * (kStageB >> 4);
+            const uint32_t a_lo = smem_lo + st * (static_cast<uint32_t>(slot_b) >> 4);
             const uint32_t b_lo = a_lo + (kAB >> 4);
             if (!no_mma) {
 #pragma unroll
@@ -1006,7 +1082,7 @@ conv_tcgen05_kernel(const __grid_constant__ CUtensorMap tmapA, const __grid_cons
         const uint2* rowA = img_base + static_cast<size_t>(okA ? ihA : 0) * Wd;
         const uint2* rowB = img_base + static_cast<size_t>(okB ? ihB : 0) * Wd;
         mbar_wait(smem_u32(&empty_bar[ps.stage]), ps.phase ^ 1);
-        const uint32_t a_row = smem_u32(smem + ps.stage * C::kStageBytes + t * 128);
+        const uint32_t a_row = smem_u32(smem + ps.stage * slot_b + t * 128);
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const uint2* rowp = u < 2 ? rowA : rowB;
@@ -1757,6 +1833,11 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   L.two = two ? 1 : 0;
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two, kb);
   L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two, kb);
+  // 64-wide tiles with a K loop: two K blocks per pipeline slot (half as many barrier rounds); at least two slots
+  if (block_n <= (tuning_env("TLXCV_KGROUP_128") ? 128 : 64) && kb == kBlockK && mode != kModeGatherC4 && !two && p.num_kb >= 4 && p.stages >= 4 && !tuning_env("TLXCV_NO_KGROUP")) {
+    p.kgroup = 2;
+    p.stages /= 2;
+  }
   const long long tiles = two ? static_cast<long long>((p.m_tiles + 1) / 2) * p.n_tiles : static_cast<long long>(p.m_tiles) * p.n_tiles;
   L.grid = two ? 2 * static_cast<int>(std::min<long long>(tiles, sm_count / 2)) : static_cast<int>(std::min<long long>(tiles, sm_count));
 

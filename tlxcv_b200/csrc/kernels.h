@@ -57,7 +57,8 @@ struct ConvKernelParams {
   int R, KR;  // filter height; K elements reserved per filter row (16 or 32)
   // shared-memory configuration chosen per layer
   int ablate;  // debug: TLXCV_DEBUG_ABLATE bit mask (timing experiments; 0 in normal operation)
-  int stages, ring;  // operand pipeline stages; epilogue store/residual ring depth per warp (2 or 4)
+  int stages, ring;  // operand pipeline slots (barrier pairs); epilogue store/residual ring depth per warp (2 or 4)
+  int kgroup;        // K blocks per pipeline slot: 1, or 2 for 64-wide tiles with >= 4 K blocks (0 = 1)
   int sc_bufs;       // scale/shift smem buffers: 1 (filled once, or unused) or 2 (refreshed per tile)
   int epi_warps;     // epilogue warps taking part: 8 or 16
   // dual-accumulator launches (conv3 + downsample conv of a stage's first block in one kernel)
