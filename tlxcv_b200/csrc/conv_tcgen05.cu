@@ -1834,7 +1834,8 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two, kb);
   L.smem = smem_for(block_n, p.ring, p.sc_bufs, p.epi_warps, two, kb);
   // 64-wide tiles with a K loop: two K blocks per pipeline slot (half as many barrier rounds); at least two slots
-  if (block_n <= (tuning_env("TLXCV_KGROUP_128") ? 128 : 64) && mode != kModeGatherC4 && !two && p.num_kb >= 4 && p.stages >= 4 && !tuning_env("TLXCV_NO_KGROUP")) {
+  if (block_n <= (tuning_env("TLXCV_KGROUP_128") ? 128 : 64) && mode != kModeGatherC4 && !two && p.num_kb >= (tuning_env("TLXCV_KGROUP_MIN_KB") ? atoi(tuning_env("TLXCV_KGROUP_MIN_KB")) : 4) && p.stages >= 4 &&
+      !tuning_env("TLXCV_NO_KGROUP")) {
     p.kgroup = 2;
     p.stages /= 2;
   }
