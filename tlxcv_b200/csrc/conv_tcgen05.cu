@@ -1829,6 +1829,9 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // 128-wide pairs measured: no gain.  Few M tiles (7x7 maps: 98) pair only with a long K loop: bs256 512->512 3x3
   // 63.5 -> 57.3 us, 2048->512 33.8 -> 31.7 us, but 512->2048 + residual (8 K blocks) 38.9 -> 43.9 us.
   bool two = pairable && kb == kBlockK && block_n == 256 && ((p.num_kb >= 8 && p.m_tiles >= 256) || (p.num_kb >= 16 && p.m_tiles >= 64));
+  // 128-wide 3x3 layers on very large maps (DarkNet / YOLOv3 at 608x608: 64 -> 128 at 152x152, 304 -> 152): bound by the
+  // operand feed, the pair halves the weight bytes per SM: 0.36 -> 0.32 / 0.37 -> 0.35 ms (ResNet-50's 28x28 layers: no gain)
+  if (pairable && kb == kBlockK && block_n == 128 && mode == kModeIm2col && p.num_kb >= 8 && p.m_tiles >= 4096) two = true;
   if (const char* e = tuning_env("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && kb == kBlockK && p.m_tiles >= 2;
   L.two = two ? 1 : 0;
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two, kb);
