@@ -223,9 +223,10 @@ class AvgPool2d(Module):
     """``padding="SAME"`` pads only where the windows do not tile the map (ceil mode, zeros excluded from the count is what
     tensorlayerx's torch backend does [recalled]); the hot path only meets maps the 2x2 / stride-2 windows tile exactly."""
 
-    def __init__(self, kernel_size=(2, 2), stride=(2, 2), padding="SAME", data_format="channels_last", name=None):
+    def __init__(self, kernel_size=(2, 2), stride=(2, 2), padding="SAME", data_format="channels_last", ceil_mode=False,
+                 name=None):
         super().__init__(name)
-        self.kernel_size, self.stride, self.padding = kernel_size, stride, padding
+        self.kernel_size, self.stride, self.padding, self.ceil_mode = kernel_size, stride, padding, ceil_mode
 
     def forward(self, x):
         k = self.kernel_size if isinstance(self.kernel_size, int) else self.kernel_size[0]
@@ -234,7 +235,7 @@ class AvgPool2d(Module):
             if (x.shape[2] - k) % st or (x.shape[3] - k) % st:
                 raise NotImplementedError("AvgPool2d(padding='SAME') on a map the windows do not tile")
             return F.avg_pool2d(x, k, st, 0)
-        return F.avg_pool2d(x, k, st, self.padding)
+        return F.avg_pool2d(x, k, st, self.padding, ceil_mode=bool(self.ceil_mode))
 
 
 class AdaptiveAvgPool2d(Module):

@@ -446,9 +446,13 @@ class AvgPool2d(Module):
     """``nn.AvgPool2d(kernel_size, stride, padding)``; ``padding="SAME"`` is accepted where it adds nothing (windows that tile
     the map exactly: the 2x2 / stride-2 pool of ResNet_vd's shortcut on even maps, segmentation/backbones/resnet_vd.py:25-27)."""
 
-    def __init__(self, kernel_size=(2, 2), stride=(2, 2), padding="SAME", data_format="channels_first", name=None):
+    def __init__(self, kernel_size=(2, 2), stride=(2, 2), padding="SAME", data_format="channels_first", ceil_mode=False,
+                 name=None):
         super().__init__(name)
         _check_format(data_format)
+        # ceil_mode (classification/resnest.py:270-276, the dilated variants' 1x1 / stride-1 pool) only matters where the
+        # windows do not tile the map, which the trace refuses anyway
+        self.ceil_mode = bool(ceil_mode)
         self.kernel_size = _pair(kernel_size, "kernel_size")
         self.stride = _pair(stride, "stride")
         if isinstance(padding, str):
