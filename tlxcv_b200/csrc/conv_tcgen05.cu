@@ -1832,6 +1832,11 @@ std::string tc_conv_prepare(TcConvLaunch& L, int sm_count, const __nv_bfloat16* 
   // 128-wide 3x3 layers on very large maps (DarkNet / YOLOv3 at 608x608: 64 -> 128 at 152x152, 304 -> 152): bound by the
   // operand feed, the pair halves the weight bytes per SM: 0.36 -> 0.32 / 0.37 -> 0.35 ms (ResNet-50's 28x28 layers: no gain)
   if (pairable && kb == kBlockK && block_n == 128 && mode == kModeIm2col && p.num_kb >= 8 && p.m_tiles >= 4096) two = true;
+  // measured again after the MMA-issue and epilogue work (ResNet-50 bs256): 128-wide layers with >= 8 K blocks gain 3-7 %
+  // as pairs (3x3 stride-2 128->128 86.6 -> 80.8 us, 1x1 512->128 54.3 -> 52.3), a 256-wide 1x1 WITHOUT a residual gains
+  // 10 % on 98 M tiles (512->2048: 37.9 -> 33.9), with a residual it loses (54 -> 60 on 14x14, 41.9 -> 43.8 on 7x7)
+  if (pairable && kb == kBlockK && block_n == 128 && p.num_kb >= 8 && p.m_tiles >= 256) two = true;
+  if (pairable && kb == kBlockK && block_n == 256 && p.num_kb >= 8 && p.m_tiles >= 64 && residual_bf16 == nullptr) two = true;
   if (const char* e = tuning_env("TLXCV_DEBUG_2SM")) two = atoi(e) != 0 && pairable && kb == kBlockK && p.m_tiles >= 2;
   L.two = two ? 1 : 0;
   choose_epilogue(p, block_n, residual_bf16 != nullptr, out_bf16 != nullptr, two, kb);
